@@ -1,0 +1,167 @@
+/*
+ * loexec.h — C ABI of libloexec.so, the B200-native (sm_100a) executor for
+ * learningOrchestra's projection -> type-cast -> histogram hot path.
+ *
+ * The reference has no native boundary on this path: it crosses from Python
+ * into py4j/JVM (Spark) and pymongo/mongod.  Each entry point below names the
+ * reference call site whose work it replaces (paths relative to
+ * /root/reference/microservices):
+ *
+ *   lo_project_cast*        projection_image/projection.py:35-46   (load/filter/select/write)
+ *                           data_type_handler_image/data_type_update.py:30-43 (per-value cast)
+ *   lo_project_cast_hist*   the two above fused with
+ *                           histogram_image/histogram.py:28-42     ($group/$sum:1 per field)
+ *   lo_hist_u8_cols*        histogram_image/histogram.py:31-36 on byte columns
+ *                           ($group value counts == 256 unit-width bins)
+ *   lo_table_*              database_api_image/database.py:124-151 (the table the path reads;
+ *                           here: columnar slabs resident in HBM instead of Mongo documents)
+ *
+ * Conventions
+ *   - every function returns LO_OK (0) or a negative LO_ERR_*; the message of
+ *     the last failure on the calling thread is lo_last_error().
+ *   - plain C types only.  `stream` arguments are a cudaStream_t passed as
+ *     void* (NULL = the context's own stream).  Functions whose name ends in
+ *     `_dev` are asynchronous on `stream` and touch only device memory;
+ *     all others synchronise before returning.
+ *   - the caller owns every host buffer; the library owns device allocations
+ *     behind lo_table handles and never keeps a host pointer after return.
+ *   - there is NO CPU fallback: without a usable CUDA device lo_init fails with
+ *     LO_ERR_NO_DEVICE and nothing else can be called.
+ *   - re-entrant: no mutable global state except the thread-local error string;
+ *     concurrent calls on one lo_ctx are allowed when they use different streams.
+ */
+#ifndef LOEXEC_H
+#define LOEXEC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LO_ABI_VERSION 1
+
+#define LO_OK                    0
+#define LO_ERR_INVALID          -1   /* bad argument (message says which)              */
+#define LO_ERR_CUDA             -2   /* a CUDA runtime call failed                      */
+#define LO_ERR_NOMEM            -3   /* device or pinned-host allocation failed         */
+#define LO_ERR_NOT_IMPLEMENTED  -4
+#define LO_ERR_NO_DEVICE        -5   /* no CUDA device / wrong architecture             */
+#define LO_ERR_ALIGNMENT        -6   /* external device pointer not 32-byte aligned     */
+
+/* element types of a columnar table */
+#define LO_F64 1   /* IEEE binary64 */
+#define LO_F32 2   /* IEEE binary32 */
+#define LO_U8  3   /* unsigned byte */
+
+/* synthetic generators (oracle/synth.py and oracle/bsem.c hold the CPU twins) */
+#define LO_SYNTH_UNIFORM   0  /* f64: lo + (hi-lo) * (splitmix64(...)>>11) * 2^-53            */
+#define LO_SYNTH_EDGES     1  /* UNIFORM + special values at row % 1000003 == col            */
+#define LO_SYNTH_CONSTCOL  2  /* EDGES + column 0 constant (contention worst case)           */
+#define LO_SYNTH_MNIST_U8  3  /* u8: 28x28 image columns, border 0, ~80 % zeros overall      */
+
+#define LO_MAX_BINS 256       /* per-thread byte-counter histograms hold <= 256 bins          */
+
+typedef struct lo_ctx   lo_ctx;    /* one per (process, device) */
+typedef struct lo_table lo_table;  /* columnar table: ncols slabs of nrows elements, one dtype */
+
+/* Fixed-width histogram request (B-semantics):
+ *   for projected column j with range [lo[j], hi[j]] (fp32) and nbins bins, over the
+ *   CAST fp32 value x:  skip NaN and x outside [lo,hi];  w = (hi-lo)/nbins (fp32 RN);
+ *   i = (int)((x-lo)/w) (fp32 RN sub, fp32 RN div, truncate);  i = min(i, nbins-1).
+ *   lo/hi are HOST arrays of k floats.  Counts are uint64, layout [k][nbins]. */
+typedef struct lo_hist_spec {
+    int32_t      nbins;     /* 1..LO_MAX_BINS */
+    int32_t      reserved;  /* must be 0 */
+    const float *lo;        /* k lower edges  */
+    const float *hi;        /* k upper edges (closed) ; hi[j] > lo[j], both finite */
+} lo_hist_spec;
+
+/* per-call device timing filled by the *_host entry points (milliseconds) */
+typedef struct lo_host_timing {
+    double total_ms;   /* wall time inside the call                      */
+    double h2d_bytes;  /* bytes copied host -> device                    */
+    double d2h_bytes;  /* bytes copied device -> host                    */
+    int64_t launches;  /* kernels launched                               */
+} lo_host_timing;
+
+/* ---- context ------------------------------------------------------------------------- */
+int         lo_abi_version(void);
+const char *lo_last_error(void);
+int         lo_device_count(int *out);
+int         lo_init(int device, lo_ctx **out);
+int         lo_shutdown(lo_ctx *ctx);
+int         lo_ctx_device(const lo_ctx *ctx, int *device, int *sm_count, size_t *hbm_bytes);
+int         lo_sync(lo_ctx *ctx, void *stream);
+/* number of kernels this context has launched since lo_init (bench "gpu_launches") */
+int         lo_launch_count(const lo_ctx *ctx, int64_t *out);
+
+/* ---- pinned host memory (so *_host calls can overlap copies with kernels) ------------ */
+int lo_host_alloc(lo_ctx *ctx, size_t bytes, void **out);
+int lo_host_free(lo_ctx *ctx, void *p);
+
+/* ---- tables --------------------------------------------------------------------------- */
+/* library-owned table: each column slab is 256-byte aligned (pitch rounded up) */
+int lo_table_alloc(lo_ctx *ctx, int dtype, int64_t nrows, int32_t ncols, lo_table **out);
+/* wrap caller-owned device memory (e.g. a torch tensor): column j starts at
+ * base + j*pitch_bytes.  Not freed by lo_table_free. */
+int lo_table_wrap(lo_ctx *ctx, int dtype, int64_t nrows, int32_t ncols,
+                  void *base_dev, int64_t pitch_bytes, lo_table **out);
+int lo_table_free(lo_ctx *ctx, lo_table *t);
+int lo_table_info(const lo_table *t, int *dtype, int64_t *nrows, int32_t *ncols,
+                  int64_t *pitch_bytes, void **base_dev);
+/* host <-> device, one column slab (or a row range of it) at a time; synchronous */
+int lo_table_upload_col(lo_ctx *ctx, lo_table *t, int32_t col, int64_t row0,
+                        const void *host, int64_t nrows);
+int lo_table_download_col(lo_ctx *ctx, const lo_table *t, int32_t col, int64_t row0,
+                          void *host, int64_t nrows);
+/* fill every column on the device with the counter-based generator; row r of this table is
+ * global row (row_offset + r), so any shard regenerates its own range. */
+int lo_table_fill_synthetic_dev(lo_ctx *ctx, lo_table *t, int kind, uint64_t seed,
+                                int64_t row_offset, double lo, double hi, void *stream);
+/* position-weighted 64-bit checksum of one column slab's bit patterns:
+ *   sum_r  bits(x[r]) * (2*(row_offset+r)+1)  mod 2^64   (bits zero-extended to 64) */
+int lo_table_checksum(lo_ctx *ctx, const lo_table *t, int32_t col, int64_t row_offset,
+                      uint64_t *out);
+
+/* ---- the hot path, device-resident ------------------------------------------------------ */
+/* out[j][r] = cast(in[col_idx[j]][r]) for j < k.  in: LO_F64.  out: LO_F32 (fp64->fp32 RNE,
+ * NaN -> 0x7fc00000) or LO_F64 (plain copy).  out->ncols >= k, out->nrows == in->nrows. */
+int lo_project_cast_dev(lo_ctx *ctx, const lo_table *in, const int32_t *col_idx, int32_t k,
+                        lo_table *out, void *stream);
+/* fused: projection + cast + per-column histogram of the cast value.  out may be NULL
+ * (histogram only).  counts_dev: device uint64[k*nbins], ACCUMULATED into (caller zeroes,
+ * e.g. with lo_counts_zero_dev) so shards / chunks add up. */
+int lo_project_cast_hist_dev(lo_ctx *ctx, const lo_table *in, const int32_t *col_idx, int32_t k,
+                             lo_table *out, const lo_hist_spec *spec, uint64_t *counts_dev,
+                             void *stream);
+/* per-column 256-bin value counts of LO_U8 columns; counts_dev: uint64[k*256], accumulated */
+int lo_hist_u8_cols_dev(lo_ctx *ctx, const lo_table *in, const int32_t *col_idx, int32_t k,
+                        uint64_t *counts_dev, void *stream);
+/* device scratch for counts */
+int lo_counts_alloc(lo_ctx *ctx, int64_t n, uint64_t **out_dev);
+int lo_counts_free(lo_ctx *ctx, uint64_t *counts_dev);
+int lo_counts_zero_dev(lo_ctx *ctx, uint64_t *counts_dev, int64_t n, void *stream);
+int lo_counts_download(lo_ctx *ctx, const uint64_t *counts_dev, int64_t n, uint64_t *host,
+                       void *stream);
+
+/* ---- the hot path, host buffers in / host buffers out (what the plugin calls) ----------- */
+/* in_cols[j]  : host pointer to the nrows doubles of projected column j (already selected by
+ *               the caller: the document->column gather is the adapter's job)
+ * out_cols[j] : host pointer receiving nrows floats, or out_cols == NULL for histogram only
+ * spec        : NULL for projection+cast only
+ * counts      : host uint64[k*nbins], overwritten
+ * Rows are streamed through the device in chunks on three streams (H2D / kernel / D2H);
+ * copies overlap kernels when the host buffers are pinned (lo_host_alloc). */
+int lo_project_cast_hist_host(lo_ctx *ctx, const double *const *in_cols, int64_t nrows, int32_t k,
+                              float *const *out_cols, const lo_hist_spec *spec, uint64_t *counts,
+                              lo_host_timing *timing);
+/* in_cols[j]: host pointer to nrows bytes; counts: host uint64[k*256], overwritten */
+int lo_hist_u8_cols_host(lo_ctx *ctx, const uint8_t *const *in_cols, int64_t nrows, int32_t k,
+                         uint64_t *counts, lo_host_timing *timing);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LOEXEC_H */

@@ -1,0 +1,398 @@
+// kernels.cuh — sm_100a device code of libloexec: projection + cast + histogram.
+//
+// Replaces (reference paths under /root/reference/microservices):
+//   projection_image/projection.py:38-43          column subset copy        -> K1
+//   data_type_handler_image/data_type_update.py:40-43  per-value cast       -> K2 (B-semantics: fp64->fp32 RNE)
+//   histogram_image/histogram.py:31-36            per-field value counting  -> K3/K4
+//
+// Design:
+//   * table = columnar slabs in HBM; a work tile is (projected column j, kTileRows rows).
+//   * every thread streams 32-byte (LDG.E.256) vectors of its column slab with
+//     L1::no_allocate / L2::evict_first, converts, and streams the result out with st.cs.
+//   * histogram = PRIVATE PER-THREAD BYTE COUNTERS in shared memory, laid out so that
+//     thread t only ever touches bank (t % 32): word w of thread t lives at smem word
+//     w*kThreads + t.  Increment = plain LDS.U8 / IADD / STS.U8 — no atomics, no bank
+//     conflicts, and the cost is independent of the value distribution (a constant column
+//     is as fast as a uniform one).  A thread handles <= 255 elements per tile so a byte
+//     never wraps; the CTA then folds the 256 private histograms with packed 16-bit adds
+//     + warp shuffles and issues one RED.64 per non-empty bin.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace lo {
+
+constexpr int kThreads      = 256;                 // threads per CTA
+constexpr int kVec          = 4;                   // f64 elements per 32-byte load
+constexpr int kBatch        = 4;                   // vector loads in flight per thread
+constexpr int kBatches      = 15;
+constexpr int kVecPerThread = kBatch * kBatches;   // 60
+constexpr int kElemsPerThread = kVec * kVecPerThread;      // 240 <= 255 (byte counter bound)
+constexpr int kTileRows     = kThreads * kElemsPerThread;  // 61440 rows per tile
+constexpr int kHistRows     = 64;                  // smem words per thread (256 bins / 4)
+constexpr int kHistSmemBytes = (kHistRows * kThreads + 256) * 4;   // 66560 B -> 3 CTAs / SM
+
+constexpr int kU8VecBytes   = 16;
+constexpr int kU8Batch      = 5;
+constexpr int kU8Batches    = 3;
+constexpr int kU8ElemsPerThread = kU8VecBytes * kU8Batch * kU8Batches;  // 240
+constexpr int kU8TileRows   = kThreads * kU8ElemsPerThread;             // 61440
+
+constexpr int kMaxColsF64   = 128;   // projected columns per launch (by-value kernel parameter)
+constexpr int kMaxColsU8    = 1024;
+
+struct ColsF64 {
+    int32_t k;
+    int32_t nbins;
+    int32_t col[kMaxColsF64];
+    float   lo[kMaxColsF64];
+    float   hi[kMaxColsF64];
+    float   w[kMaxColsF64];
+};
+
+struct ColsU8 {
+    int32_t k;
+    int32_t col[kMaxColsU8];
+};
+
+// ---------------------------------------------------------------------------------------------
+// streaming memory ops
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ldg256_stream(const double *p, double (&v)[4]) {
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+}
+__device__ __forceinline__ double ldg64_stream(const double *p) {
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint4 ldg128_stream(const uint8_t *p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint32_t ldg8_stream(const uint8_t *p) {
+    uint32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.u8 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void stg128_stream(float *p, float a, float b, float c, float d) {
+    asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" :: "l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void stg256_stream(double *p, const double (&v)[4]) {
+    asm volatile("st.global.cs.v4.f64 [%0], {%1,%2,%3,%4};" :: "l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// element semantics (the CPU twins are oracle/bsem.c and oracle/bsem_numpy.py)
+// ---------------------------------------------------------------------------------------------
+// fp64 -> fp32 round-to-nearest-even; every NaN becomes the canonical quiet NaN 0x7fc00000.
+__device__ __forceinline__ float cast_f64_f32(double x) {
+    float f = __double2float_rn(x);
+    return (f != f) ? __int_as_float(0x7fc00000) : f;
+}
+
+// byte offset of bin b inside a thread's private histogram (before OR-ing in 4*tid):
+// word row (b >> 2) at stride kThreads words, byte (b & 3).  For kThreads == 256 the row
+// offset is (b & 0xFC) << 8, so offset = (b * 0x101) & 0xFC03 and never overlaps 4*tid (bits 2..9).
+static_assert(kThreads == 256, "private histogram addressing assumes 256 threads");
+__device__ __forceinline__ uint32_t bin_byte_offset(uint32_t b) { return (b * 0x101u) & 0xFC03u; }
+
+__device__ __forceinline__ void bump(uint8_t *priv /* smem + 4*tid */, uint32_t b) {
+    uint8_t *p = priv + bin_byte_offset(b);
+    *p = (uint8_t)(*p + 1);
+}
+
+// fixed-width binning of the CAST value: fp32 RN subtract, fp32 RN divide,
+// truncate, close the last bin.  NaN and out-of-range values are skipped.
+__device__ __forceinline__ void bin_f32(uint8_t *priv, float f, float lo, float hi, float w, int last) {
+    if (f >= lo && f <= hi) {
+        float t = __fdiv_rn(__fsub_rn(f, lo), w);
+        int   i = __float2int_rz(t);
+        bump(priv, (uint32_t)min(i, last));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// CTA-wide fold of the private byte histograms -> RED.64 into counts[]
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void zero_private(uint32_t *smem, int rows) {
+    for (int w = 0; w < rows; ++w) smem[w * kThreads + threadIdx.x] = 0u;
+}
+
+// Each private byte is <= 255 and a row holds kThreads = 256 words: a lane sums 8 words into
+// packed 16-bit halves (<= 2040), the 32-lane butterfly keeps them <= 65280 — no overflow.
+__device__ __forceinline__ void fold_and_flush(uint32_t *smem, int rows, int nbins,
+                                               unsigned long long *counts /* this column's bins */) {
+    uint32_t *folded = smem + kHistRows * kThreads;   // 256 words
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    for (int w = warp; w < rows; w += kThreads / 32) {
+        const uint32_t *row = smem + w * kThreads;
+        uint32_t even = 0, odd = 0;
+#pragma unroll
+        for (int i = 0; i < kThreads / 32; ++i) {
+            uint32_t x = row[lane + 32 * i];
+            even += x & 0x00FF00FFu;
+            odd  += (x >> 8) & 0x00FF00FFu;
+        }
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            even += __shfl_xor_sync(0xffffffffu, even, s);
+            odd  += __shfl_xor_sync(0xffffffffu, odd, s);
+        }
+        if (lane == 0) {
+            folded[4 * w + 0] = even & 0xFFFFu;
+            folded[4 * w + 1] = odd & 0xFFFFu;
+            folded[4 * w + 2] = even >> 16;
+            folded[4 * w + 3] = odd >> 16;
+        }
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < nbins) {
+        uint32_t c = folded[threadIdx.x];
+        if (c) atomicAdd(counts + threadIdx.x, (unsigned long long)c);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1+K2+K3: fused projection + cast + histogram over f64 column slabs
+//   OUT: 0 = no projected output (histogram only), 1 = f32 (cast), 2 = f64 (copy)
+//   HIST: accumulate per-column fixed-width histogram of the cast value
+//   ALIGNED: column slabs (in and out) are 32-byte aligned -> 256-bit loads, 128/256-bit stores
+// grid.x = k * tiles_per_col ; tile index fastest along rows
+// ---------------------------------------------------------------------------------------------
+template <int OUT, bool HIST, bool ALIGNED>
+__global__ void __launch_bounds__(kThreads, 3)
+k_project_cast_hist(const char *__restrict__ in_base, long long in_pitch,
+                    char *__restrict__ out_base, long long out_pitch,
+                    long long nrows, unsigned tiles_per_col,
+                    unsigned long long *__restrict__ counts,
+                    const __grid_constant__ ColsF64 P) {
+    extern __shared__ uint32_t smem[];
+    const unsigned j    = blockIdx.x / tiles_per_col;
+    const unsigned tile = blockIdx.x - j * tiles_per_col;
+    const long long r0  = (long long)tile * kTileRows;
+    const long long n   = min((long long)kTileRows, nrows - r0);   // rows in this tile (> 0)
+
+    const double *in = reinterpret_cast<const double *>(in_base + (long long)P.col[j] * in_pitch) + r0;
+    float  *out32 = nullptr;
+    double *out64 = nullptr;
+    if (OUT == 1) out32 = reinterpret_cast<float *>(out_base + (long long)j * out_pitch) + r0;
+    if (OUT == 2) out64 = reinterpret_cast<double *>(out_base + (long long)j * out_pitch) + r0;
+
+    float lo = 0.f, hi = 0.f, w = 1.f;
+    int rows = 0, last = 0;
+    uint8_t *priv = reinterpret_cast<uint8_t *>(smem) + 4 * threadIdx.x;
+    if (HIST) {
+        lo = P.lo[j]; hi = P.hi[j]; w = P.w[j];
+        last = P.nbins - 1;
+        rows = (P.nbins + 3) >> 2;
+        zero_private(smem, rows);
+        // a thread only touches its own words until fold_and_flush: no barrier needed here
+    }
+
+    if (ALIGNED) {
+#pragma unroll 1
+        for (int b = 0; b < kBatches; ++b) {
+            const long long e0 = ((long long)b * kBatch * kThreads + threadIdx.x) * kVec;   // first element of vector 0
+            if (e0 >= n) break;
+            double v[kBatch][4];
+            if (e0 + (long long)(kBatch - 1) * kThreads * kVec + kVec <= n) {
+                // whole batch in range: all loads first (MLP), then convert/store/bin
+#pragma unroll
+                for (int u = 0; u < kBatch; ++u) ldg256_stream(in + e0 + (long long)u * kThreads * kVec, v[u]);
+#pragma unroll
+                for (int u = 0; u < kBatch; ++u) {
+                    const long long e = e0 + (long long)u * kThreads * kVec;
+                    float f0 = cast_f64_f32(v[u][0]), f1 = cast_f64_f32(v[u][1]);
+                    float f2 = cast_f64_f32(v[u][2]), f3 = cast_f64_f32(v[u][3]);
+                    if (OUT == 1) stg128_stream(out32 + e, f0, f1, f2, f3);
+                    if (OUT == 2) stg256_stream(out64 + e, v[u]);
+                    if (HIST) {
+                        bin_f32(priv, f0, lo, hi, w, last); bin_f32(priv, f1, lo, hi, w, last);
+                        bin_f32(priv, f2, lo, hi, w, last); bin_f32(priv, f3, lo, hi, w, last);
+                    }
+                }
+            } else {
+                // ragged end of the column: element-wise
+#pragma unroll 1
+                for (int u = 0; u < kBatch; ++u) {
+                    const long long e = e0 + (long long)u * kThreads * kVec;
+#pragma unroll 1
+                    for (int q = 0; q < kVec; ++q) {
+                        if (e + q < n) {
+                            double x = ldg64_stream(in + e + q);
+                            float  f = cast_f64_f32(x);
+                            if (OUT == 1) out32[e + q] = f;
+                            if (OUT == 2) out64[e + q] = x;
+                            if (HIST) bin_f32(priv, f, lo, hi, w, last);
+                        }
+                    }
+                }
+            }
+        }
+    } else {
+        // unaligned slabs (wrapped foreign memory): scalar, lane-contiguous accesses
+#pragma unroll 1
+        for (int i = 0; i < kElemsPerThread; ++i) {
+            const long long e = (long long)i * kThreads + threadIdx.x;
+            if (e >= n) break;
+            double x = ldg64_stream(in + e);
+            float  f = cast_f64_f32(x);
+            if (OUT == 1) out32[e] = f;
+            if (OUT == 2) out64[e] = x;
+            if (HIST) bin_f32(priv, f, lo, hi, w, last);
+        }
+    }
+
+    if (HIST) fold_and_flush(smem, rows, P.nbins, counts + (long long)j * P.nbins);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4: per-column 256-bin value counts of byte columns
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bump_word(uint8_t *priv, uint32_t x) {
+    bump(priv, x & 0xFFu); bump(priv, (x >> 8) & 0xFFu);
+    bump(priv, (x >> 16) & 0xFFu); bump(priv, x >> 24);
+}
+
+template <bool ALIGNED>
+__global__ void __launch_bounds__(kThreads, 3)
+k_hist_u8_cols(const uint8_t *__restrict__ in_base, long long in_pitch, long long nrows,
+               unsigned tiles_per_col, unsigned long long *__restrict__ counts,
+               const __grid_constant__ ColsU8 P) {
+    extern __shared__ uint32_t smem[];
+    const unsigned j    = blockIdx.x / tiles_per_col;
+    const unsigned tile = blockIdx.x - j * tiles_per_col;
+    const long long r0  = (long long)tile * kU8TileRows;
+    const long long n   = min((long long)kU8TileRows, nrows - r0);
+    const uint8_t *in   = in_base + (long long)P.col[j] * in_pitch + r0;
+    uint8_t *priv = reinterpret_cast<uint8_t *>(smem) + 4 * threadIdx.x;
+    zero_private(smem, kHistRows);
+
+    if (ALIGNED) {
+#pragma unroll 1
+        for (int b = 0; b < kU8Batches; ++b) {
+            const long long e0 = ((long long)b * kU8Batch * kThreads + threadIdx.x) * kU8VecBytes;
+            if (e0 >= n) break;
+            if (e0 + (long long)(kU8Batch - 1) * kThreads * kU8VecBytes + kU8VecBytes <= n) {
+                uint4 v[kU8Batch];
+#pragma unroll
+                for (int u = 0; u < kU8Batch; ++u) v[u] = ldg128_stream(in + e0 + (long long)u * kThreads * kU8VecBytes);
+#pragma unroll
+                for (int u = 0; u < kU8Batch; ++u) {
+                    bump_word(priv, v[u].x); bump_word(priv, v[u].y);
+                    bump_word(priv, v[u].z); bump_word(priv, v[u].w);
+                }
+            } else {
+#pragma unroll 1
+                for (int u = 0; u < kU8Batch; ++u) {
+                    const long long e = e0 + (long long)u * kThreads * kU8VecBytes;
+#pragma unroll 1
+                    for (int q = 0; q < kU8VecBytes; ++q)
+                        if (e + q < n) bump(priv, ldg8_stream(in + e + q));
+                }
+            }
+        }
+    } else {
+#pragma unroll 1
+        for (int i = 0; i < kU8ElemsPerThread; ++i) {
+            const long long e = (long long)i * kThreads + threadIdx.x;
+            if (e >= n) break;
+            bump(priv, ldg8_stream(in + e));
+        }
+    }
+    fold_and_flush(smem, kHistRows, 256, counts + (long long)j * 256);
+}
+
+// ---------------------------------------------------------------------------------------------
+// synthetic tables (bench / parity inputs) — CPU twins: oracle/bsem.c, oracle/synth.py
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+constexpr int kSpecialPeriod = 1009;
+constexpr int kNumSpecials   = 20;
+
+__device__ __forceinline__ double special_value(int idx, double lo, double hi) {
+    switch (idx) {
+        case 0:  return 0.0;
+        case 1:  return -0.0;
+        case 2:  return 1e-40;                                  // fp32 subnormal
+        case 3:  return 1e-46;                                  // underflows to +0
+        case 4:  return -1e-46;                                 // underflows to -0
+        case 5:  return 1e39;                                   // overflows to +inf
+        case 6:  return -1e39;
+        case 7:  return __longlong_as_double(0x7ff8000000000000ll);   // quiet NaN
+        case 8:  return __longlong_as_double(0xfff4000000000001ll);   // negative signalling NaN with payload
+        case 9:  return 1.0 + 5.9604644775390625e-08;           // 1 + 2^-24 : RNE tie -> 1.0
+        case 10: return 1.0 + 1.7881393432617188e-07;           // 1 + 3*2^-24 : tie -> 1 + 2^-22
+        case 11: return 16777217.0;                             // 2^24 + 1 : tie -> 2^24
+        case 12: return 3.4028235677973366e38;                  // tie at FLT_MAX boundary -> +inf
+        case 13: return hi;
+        case 14: return lo;
+        case 15: return __longlong_as_double(__double_as_longlong(hi) + (hi > 0 ? 1 : -1));   // next above hi (hi != 0)
+        case 16: return __dadd_rn(hi, __dmul_rn(hi - lo, 9.5367431640625e-07));    // clearly above hi (no FMA)
+        case 17: return __dsub_rn(lo, __dmul_rn(hi - lo, 9.5367431640625e-07));    // clearly below lo (no FMA)
+        case 18: return __longlong_as_double(0x7ff0000000000000ll);   // +inf
+        default: return __longlong_as_double(0xfff0000000000000ll);   // -inf
+    }
+}
+
+__global__ void k_fill_f64(double *base, long long pitch_elems, long long nrows, int ncols,
+                           int kind, uint64_t seed, long long row_offset, double lo, double hi) {
+    const long long total = nrows * (long long)ncols;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int       c = (int)(i / nrows);
+        const long long r = i - (long long)c * nrows;
+        const uint64_t  g = (uint64_t)(row_offset + r);
+        const uint64_t  u = splitmix64(seed ^ ((uint64_t)c << 40) ^ g);
+        // separate RN multiply and add (no FMA) so numpy / C reproduce it bit for bit
+        double x = __dadd_rn(lo, __dmul_rn(hi - lo, __dmul_rn((double)(u >> 11), 1.1102230246251565e-16)));
+        if (kind >= 1 && (g % kSpecialPeriod) == (uint64_t)(c % kSpecialPeriod))
+            x = special_value((int)((g / kSpecialPeriod + (uint64_t)c) % kNumSpecials), lo, hi);
+        if (kind == 2 && c == 0) x = __dadd_rn(lo, __dmul_rn(hi - lo, 0.75));
+        base[(long long)c * pitch_elems + r] = x;
+    }
+}
+
+__global__ void k_fill_u8_mnist(uint8_t *base, long long pitch, long long nrows, int ncols,
+                                uint64_t seed, long long row_offset) {
+    const long long total = nrows * (long long)ncols;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int       c = (int)(i / nrows);
+        const long long r = i - (long long)c * nrows;
+        const uint64_t  u = splitmix64(seed ^ ((uint64_t)c << 40) ^ (uint64_t)(row_offset + r));
+        const int py = (c % 784) / 28, px = (c % 784) % 28;
+        uint8_t v = 0;
+        if (py >= 4 && py < 24 && px >= 4 && px < 24 && (u & 0xFFu) >= 0x99u) v = (uint8_t)((u >> 8) & 0xFFu);
+        base[(long long)c * pitch + r] = v;
+    }
+}
+
+template <typename T>
+__global__ void k_checksum(const T *col, long long nrows, long long row_offset, unsigned long long *out) {
+    unsigned long long acc = 0;
+    for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < nrows;
+         r += (long long)gridDim.x * blockDim.x) {
+        unsigned long long bits;
+        if (sizeof(T) == 8)      bits = (unsigned long long)reinterpret_cast<const unsigned long long *>(col)[r];
+        else if (sizeof(T) == 4) bits = (unsigned long long)reinterpret_cast<const unsigned int *>(col)[r];
+        else                     bits = (unsigned long long)reinterpret_cast<const unsigned char *>(col)[r];
+        acc += bits * (2ull * (unsigned long long)(row_offset + r) + 1ull);
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}
+
+}  // namespace lo

@@ -1,0 +1,719 @@
+// loexec.cu — host side of libloexec.so: the C ABI declared in include/loexec.h.
+//
+// Nothing here computes on the CPU: every entry point either moves bytes or launches the
+// sm_100a kernels in kernels.cuh.  There is no fallback path; without a Blackwell device
+// lo_init() fails and nothing else is callable.
+#include "loexec.h"
+#include "kernels.cuh"
+
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define LO_CUDA(call)                                                                        \
+    do {                                                                                     \
+        cudaError_t e_ = (call);                                                             \
+        if (e_ != cudaSuccess) {                                                             \
+            int code_ = (e_ == cudaErrorMemoryAllocation) ? LO_ERR_NOMEM : LO_ERR_CUDA;      \
+            return fail(code_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),       \
+                        __FILE__, __LINE__);                                                 \
+        }                                                                                    \
+    } while (0)
+
+#define LO_TRY(call)                 \
+    do {                             \
+        int rc_ = (call);            \
+        if (rc_ != LO_OK) return rc_; \
+    } while (0)
+
+size_t dtype_size(int dtype) {
+    switch (dtype) {
+        case LO_F64: return 8;
+        case LO_F32: return 4;
+        case LO_U8:  return 1;
+        default:     return 0;
+    }
+}
+
+}  // namespace
+
+struct lo_table {
+    int       dtype;
+    int64_t   nrows;
+    int32_t   ncols;
+    int64_t   pitch;   // bytes between column slabs
+    char     *base;
+    bool      owned;
+    int       device;
+};
+
+struct lo_ctx {
+    int          device;
+    int          sm_count;
+    size_t       hbm_bytes;
+    cudaStream_t stream;       // default stream for NULL `stream` arguments
+    cudaStream_t h2d, d2h;     // copy streams of the *_host pipeline
+    std::atomic<int64_t> launches{0};
+    // *_host pipeline staging (one pipeline at a time per context)
+    std::mutex   host_mu;
+    char        *stage_in[2]  = {nullptr, nullptr};
+    char        *stage_out[2] = {nullptr, nullptr};
+    size_t       stage_in_bytes = 0, stage_out_bytes = 0;
+    unsigned long long *host_counts_dev = nullptr;
+    size_t       host_counts_n = 0;
+    cudaEvent_t  ev_h2d[2], ev_k[2], ev_d2h[2];
+};
+
+namespace {
+
+cudaStream_t pick(lo_ctx *ctx, void *stream) { return stream ? (cudaStream_t)stream : ctx->stream; }
+
+int check_ctx(const lo_ctx *ctx) {
+    if (!ctx) return fail(LO_ERR_INVALID, "ctx is NULL");
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return fail(LO_ERR_CUDA, "cudaSetDevice(%d): %s", ctx->device, cudaGetErrorString(e));
+    return LO_OK;
+}
+
+bool aligned32(const lo_table *t) {
+    return ((uintptr_t)t->base % 32 == 0) && (t->pitch % 32 == 0);
+}
+
+int check_cols(const lo_table *in, const int32_t *col_idx, int32_t k) {
+    if (k <= 0) return fail(LO_ERR_INVALID, "k must be > 0 (got %d)", k);
+    if (!col_idx) return fail(LO_ERR_INVALID, "col_idx is NULL");
+    for (int j = 0; j < k; ++j)
+        if (col_idx[j] < 0 || col_idx[j] >= in->ncols)
+            return fail(LO_ERR_INVALID, "col_idx[%d] = %d outside [0, %d)", j, col_idx[j], in->ncols);
+    return LO_OK;
+}
+
+int check_spec(const lo_hist_spec *spec, int32_t k, float *w_out /* k */) {
+    if (spec->nbins < 1 || spec->nbins > LO_MAX_BINS)
+        return fail(LO_ERR_INVALID, "nbins = %d outside [1, %d]", spec->nbins, LO_MAX_BINS);
+    if (spec->reserved != 0) return fail(LO_ERR_INVALID, "lo_hist_spec.reserved must be 0");
+    if (!spec->lo || !spec->hi) return fail(LO_ERR_INVALID, "lo_hist_spec.lo / .hi is NULL");
+    for (int j = 0; j < k; ++j) {
+        const float lo = spec->lo[j], hi = spec->hi[j];
+        // w = (hi - lo) / nbins in fp32 round-to-nearest, exactly as the oracle computes it
+        volatile float span = hi - lo;
+        volatile float w    = span / (float)spec->nbins;
+        if (!(std::isfinite(lo) && std::isfinite(hi)) || !(hi > lo) || !std::isfinite(w) || !(w > 0.0f))
+            return fail(LO_ERR_INVALID, "histogram range of column %d is not usable: lo=%g hi=%g nbins=%d",
+                        j, (double)lo, (double)hi, spec->nbins);
+        w_out[j] = w;
+    }
+    return LO_OK;
+}
+
+template <typename K>
+int allow_smem(K kernel) {
+    LO_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lo::kHistSmemBytes));
+    return LO_OK;
+}
+
+int configure_kernels() {
+    LO_TRY(allow_smem(lo::k_project_cast_hist<0, true, true>));
+    LO_TRY(allow_smem(lo::k_project_cast_hist<1, true, true>));
+    LO_TRY(allow_smem(lo::k_project_cast_hist<2, true, true>));
+    LO_TRY(allow_smem(lo::k_project_cast_hist<0, true, false>));
+    LO_TRY(allow_smem(lo::k_project_cast_hist<1, true, false>));
+    LO_TRY(allow_smem(lo::k_project_cast_hist<2, true, false>));
+    LO_TRY(allow_smem(lo::k_hist_u8_cols<true>));
+    LO_TRY(allow_smem(lo::k_hist_u8_cols<false>));
+    return LO_OK;
+}
+
+// one launch of the fused kernel over <= kMaxColsF64 projected columns
+template <int OUT, bool HIST>
+int launch_f64(lo_ctx *ctx, const lo_table *in, const lo_table *out, int32_t out_col0,
+               const lo::ColsF64 &P, unsigned long long *counts, bool aligned, cudaStream_t s) {
+    const unsigned tiles_per_col = (unsigned)((in->nrows + lo::kTileRows - 1) / lo::kTileRows);
+    const unsigned long long blocks = (unsigned long long)tiles_per_col * (unsigned)P.k;
+    if (blocks > 0x7fffffffull) return fail(LO_ERR_INVALID, "table too large for one launch (%llu tiles)", blocks);
+    const size_t smem = HIST ? lo::kHistSmemBytes : 0;
+    char *out_base = out ? out->base + (int64_t)out_col0 * out->pitch : nullptr;
+    const long long out_pitch = out ? out->pitch : 0;
+    if (aligned)
+        lo::k_project_cast_hist<OUT, HIST, true><<<(unsigned)blocks, lo::kThreads, smem, s>>>(
+            in->base, in->pitch, out_base, out_pitch, in->nrows, tiles_per_col, counts, P);
+    else
+        lo::k_project_cast_hist<OUT, HIST, false><<<(unsigned)blocks, lo::kThreads, smem, s>>>(
+            in->base, in->pitch, out_base, out_pitch, in->nrows, tiles_per_col, counts, P);
+    LO_CUDA(cudaGetLastError());
+    ctx->launches.fetch_add(1, std::memory_order_relaxed);
+    return LO_OK;
+}
+
+int project_cast_hist_impl(lo_ctx *ctx, const lo_table *in, const int32_t *col_idx, int32_t k,
+                           lo_table *out, const lo_hist_spec *spec, uint64_t *counts_dev, cudaStream_t s) {
+    if (!in) return fail(LO_ERR_INVALID, "input table is NULL");
+    if (in->dtype != LO_F64) return fail(LO_ERR_INVALID, "input table must be LO_F64 (got dtype %d)", in->dtype);
+    LO_TRY(check_cols(in, col_idx, k));
+    int out_mode = 0;
+    if (out) {
+        if (out->dtype == LO_F32) out_mode = 1;
+        else if (out->dtype == LO_F64) out_mode = 2;
+        else return fail(LO_ERR_INVALID, "output table must be LO_F32 or LO_F64 (got dtype %d)", out->dtype);
+        if (out->nrows != in->nrows) return fail(LO_ERR_INVALID, "output rows %lld != input rows %lld",
+                                                  (long long)out->nrows, (long long)in->nrows);
+        if (out->ncols < k) return fail(LO_ERR_INVALID, "output has %d columns, need %d", out->ncols, k);
+        if (out->device != in->device) return fail(LO_ERR_INVALID, "tables live on different devices");
+    }
+    if (!out && !spec) return fail(LO_ERR_INVALID, "nothing to do: no output table and no histogram spec");
+    std::vector<float> w;
+    if (spec) {
+        if (!counts_dev) return fail(LO_ERR_INVALID, "counts_dev is NULL");
+        w.resize(k);
+        LO_TRY(check_spec(spec, k, w.data()));
+    }
+    if (in->nrows == 0) return LO_OK;
+    const bool aligned = aligned32(in) && (!out || aligned32(out));
+
+    for (int32_t c0 = 0; c0 < k; c0 += lo::kMaxColsF64) {
+        lo::ColsF64 P;
+        P.k     = std::min<int32_t>(lo::kMaxColsF64, k - c0);
+        P.nbins = spec ? spec->nbins : 0;
+        for (int j = 0; j < P.k; ++j) {
+            P.col[j] = col_idx[c0 + j];
+            P.lo[j]  = spec ? spec->lo[c0 + j] : 0.f;
+            P.hi[j]  = spec ? spec->hi[c0 + j] : 0.f;
+            P.w[j]   = spec ? w[c0 + j] : 1.f;
+        }
+        unsigned long long *cnt = spec ? (unsigned long long *)counts_dev + (int64_t)c0 * spec->nbins : nullptr;
+        int rc;
+        if (spec) {
+            if (out_mode == 0)      rc = launch_f64<0, true>(ctx, in, out, c0, P, cnt, aligned, s);
+            else if (out_mode == 1) rc = launch_f64<1, true>(ctx, in, out, c0, P, cnt, aligned, s);
+            else                    rc = launch_f64<2, true>(ctx, in, out, c0, P, cnt, aligned, s);
+        } else {
+            if (out_mode == 1)      rc = launch_f64<1, false>(ctx, in, out, c0, P, cnt, aligned, s);
+            else                    rc = launch_f64<2, false>(ctx, in, out, c0, P, cnt, aligned, s);
+        }
+        LO_TRY(rc);
+    }
+    return LO_OK;
+}
+
+int hist_u8_impl(lo_ctx *ctx, const lo_table *in, const int32_t *col_idx, int32_t k,
+                 uint64_t *counts_dev, cudaStream_t s) {
+    if (!in) return fail(LO_ERR_INVALID, "input table is NULL");
+    if (in->dtype != LO_U8) return fail(LO_ERR_INVALID, "input table must be LO_U8 (got dtype %d)", in->dtype);
+    LO_TRY(check_cols(in, col_idx, k));
+    if (!counts_dev) return fail(LO_ERR_INVALID, "counts_dev is NULL");
+    if (in->nrows == 0) return LO_OK;
+    const bool aligned = ((uintptr_t)in->base % 16 == 0) && (in->pitch % 16 == 0);
+    const unsigned tiles_per_col = (unsigned)((in->nrows + lo::kU8TileRows - 1) / lo::kU8TileRows);
+    for (int32_t c0 = 0; c0 < k; c0 += lo::kMaxColsU8) {
+        lo::ColsU8 P;
+        P.k = std::min<int32_t>(lo::kMaxColsU8, k - c0);
+        for (int j = 0; j < P.k; ++j) P.col[j] = col_idx[c0 + j];
+        const unsigned long long blocks = (unsigned long long)tiles_per_col * (unsigned)P.k;
+        if (blocks > 0x7fffffffull) return fail(LO_ERR_INVALID, "table too large for one launch");
+        unsigned long long *cnt = (unsigned long long *)counts_dev + (int64_t)c0 * 256;
+        if (aligned)
+            lo::k_hist_u8_cols<true><<<(unsigned)blocks, lo::kThreads, lo::kHistSmemBytes, s>>>(
+                (const uint8_t *)in->base, in->pitch, in->nrows, tiles_per_col, cnt, P);
+        else
+            lo::k_hist_u8_cols<false><<<(unsigned)blocks, lo::kThreads, lo::kHistSmemBytes, s>>>(
+                (const uint8_t *)in->base, in->pitch, in->nrows, tiles_per_col, cnt, P);
+        LO_CUDA(cudaGetLastError());
+        ctx->launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    return LO_OK;
+}
+
+int ensure_stage(lo_ctx *ctx, size_t in_bytes, size_t out_bytes, size_t ncounts) {
+    if (in_bytes > ctx->stage_in_bytes) {
+        for (int i = 0; i < 2; ++i) {
+            if (ctx->stage_in[i]) cudaFree(ctx->stage_in[i]);
+            ctx->stage_in[i] = nullptr;
+        }
+        ctx->stage_in_bytes = 0;
+        for (int i = 0; i < 2; ++i) LO_CUDA(cudaMalloc((void **)&ctx->stage_in[i], in_bytes));
+        ctx->stage_in_bytes = in_bytes;
+    }
+    if (out_bytes > ctx->stage_out_bytes) {
+        for (int i = 0; i < 2; ++i) {
+            if (ctx->stage_out[i]) cudaFree(ctx->stage_out[i]);
+            ctx->stage_out[i] = nullptr;
+        }
+        ctx->stage_out_bytes = 0;
+        for (int i = 0; i < 2; ++i) LO_CUDA(cudaMalloc((void **)&ctx->stage_out[i], out_bytes));
+        ctx->stage_out_bytes = out_bytes;
+    }
+    if (ncounts > ctx->host_counts_n) {
+        if (ctx->host_counts_dev) cudaFree(ctx->host_counts_dev);
+        ctx->host_counts_dev = nullptr;
+        ctx->host_counts_n = 0;
+        LO_CUDA(cudaMalloc((void **)&ctx->host_counts_dev, ncounts * sizeof(unsigned long long)));
+        ctx->host_counts_n = ncounts;
+    }
+    return LO_OK;
+}
+
+// rows per chunk of the *_host pipeline: ~64 MiB of input per chunk, whole tiles
+int64_t chunk_rows_for(int64_t nrows, int32_t k, size_t elem_bytes, int64_t tile_rows) {
+    const int64_t target = (int64_t)((64ull << 20) / ((size_t)k * elem_bytes));
+    int64_t rows = std::max<int64_t>(tile_rows, (target / tile_rows) * tile_rows);
+    return std::min(rows, ((nrows + tile_rows - 1) / tile_rows) * tile_rows);
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+int lo_abi_version(void) { return LO_ABI_VERSION; }
+
+const char *lo_last_error(void) { return g_err.c_str(); }
+
+int lo_device_count(int *out) {
+    if (!out) return fail(LO_ERR_INVALID, "out is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        *out = 0;
+        return fail(LO_ERR_NO_DEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    *out = n;
+    return LO_OK;
+}
+
+int lo_init(int device, lo_ctx **out) {
+    if (!out) return fail(LO_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(LO_ERR_NO_DEVICE, "no CUDA device (%s); libloexec has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (device < 0 || device >= n) return fail(LO_ERR_INVALID, "device %d outside [0, %d)", device, n);
+    cudaDeviceProp prop;
+    LO_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(LO_ERR_NO_DEVICE, "device %d is sm_%d%d; libloexec is built for sm_100a only", device,
+                    prop.major, prop.minor);
+    LO_CUDA(cudaSetDevice(device));
+    lo_ctx *ctx = new (std::nothrow) lo_ctx;
+    if (!ctx) return fail(LO_ERR_NOMEM, "out of host memory");
+    ctx->device    = device;
+    ctx->sm_count  = prop.multiProcessorCount;
+    ctx->hbm_bytes = prop.totalGlobalMem;
+    LO_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    LO_CUDA(cudaStreamCreateWithFlags(&ctx->h2d, cudaStreamNonBlocking));
+    LO_CUDA(cudaStreamCreateWithFlags(&ctx->d2h, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        LO_CUDA(cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming));
+        LO_CUDA(cudaEventCreateWithFlags(&ctx->ev_k[i], cudaEventDisableTiming));
+        LO_CUDA(cudaEventCreateWithFlags(&ctx->ev_d2h[i], cudaEventDisableTiming));
+    }
+    int rc = configure_kernels();
+    if (rc != LO_OK) { delete ctx; return rc; }
+    *out = ctx;
+    return LO_OK;
+}
+
+int lo_shutdown(lo_ctx *ctx) {
+    if (!ctx) return LO_OK;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->stage_in[i]) cudaFree(ctx->stage_in[i]);
+        if (ctx->stage_out[i]) cudaFree(ctx->stage_out[i]);
+        cudaEventDestroy(ctx->ev_h2d[i]);
+        cudaEventDestroy(ctx->ev_k[i]);
+        cudaEventDestroy(ctx->ev_d2h[i]);
+    }
+    if (ctx->host_counts_dev) cudaFree(ctx->host_counts_dev);
+    cudaStreamDestroy(ctx->stream);
+    cudaStreamDestroy(ctx->h2d);
+    cudaStreamDestroy(ctx->d2h);
+    delete ctx;
+    return LO_OK;
+}
+
+int lo_ctx_device(const lo_ctx *ctx, int *device, int *sm_count, size_t *hbm_bytes) {
+    if (!ctx) return fail(LO_ERR_INVALID, "ctx is NULL");
+    if (device) *device = ctx->device;
+    if (sm_count) *sm_count = ctx->sm_count;
+    if (hbm_bytes) *hbm_bytes = ctx->hbm_bytes;
+    return LO_OK;
+}
+
+int lo_sync(lo_ctx *ctx, void *stream) {
+    LO_TRY(check_ctx(ctx));
+    LO_CUDA(cudaStreamSynchronize(pick(ctx, stream)));
+    return LO_OK;
+}
+
+int lo_launch_count(const lo_ctx *ctx, int64_t *out) {
+    if (!ctx || !out) return fail(LO_ERR_INVALID, "NULL argument");
+    *out = ctx->launches.load(std::memory_order_relaxed);
+    return LO_OK;
+}
+
+int lo_host_alloc(lo_ctx *ctx, size_t bytes, void **out) {
+    LO_TRY(check_ctx(ctx));
+    if (!out) return fail(LO_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (bytes == 0) return LO_OK;
+    LO_CUDA(cudaHostAlloc(out, bytes, cudaHostAllocPortable));
+    return LO_OK;
+}
+
+int lo_host_free(lo_ctx *ctx, void *p) {
+    LO_TRY(check_ctx(ctx));
+    if (p) LO_CUDA(cudaFreeHost(p));
+    return LO_OK;
+}
+
+// ---- tables -------------------------------------------------------------------------------------
+int lo_table_alloc(lo_ctx *ctx, int dtype, int64_t nrows, int32_t ncols, lo_table **out) {
+    LO_TRY(check_ctx(ctx));
+    if (!out) return fail(LO_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    const size_t es = dtype_size(dtype);
+    if (!es) return fail(LO_ERR_INVALID, "unknown dtype %d", dtype);
+    if (nrows < 0 || ncols <= 0) return fail(LO_ERR_INVALID, "bad shape %lld x %d", (long long)nrows, ncols);
+    const int64_t pitch = (int64_t)(((size_t)nrows * es + 255) / 256 * 256);
+    lo_table *t = new (std::nothrow) lo_table;
+    if (!t) return fail(LO_ERR_NOMEM, "out of host memory");
+    t->dtype = dtype; t->nrows = nrows; t->ncols = ncols; t->pitch = pitch;
+    t->base = nullptr; t->owned = true; t->device = ctx->device;
+    const size_t bytes = std::max<size_t>((size_t)pitch * (size_t)ncols, 256);
+    cudaError_t e = cudaMalloc((void **)&t->base, bytes);
+    if (e != cudaSuccess) {
+        delete t;
+        cudaGetLastError();
+        return fail(LO_ERR_NOMEM, "cudaMalloc(%zu bytes) for a %lld x %d table: %s", bytes, (long long)nrows,
+                    ncols, cudaGetErrorString(e));
+    }
+    *out = t;
+    return LO_OK;
+}
+
+int lo_table_wrap(lo_ctx *ctx, int dtype, int64_t nrows, int32_t ncols, void *base_dev, int64_t pitch_bytes,
+                  lo_table **out) {
+    LO_TRY(check_ctx(ctx));
+    if (!out) return fail(LO_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    const size_t es = dtype_size(dtype);
+    if (!es) return fail(LO_ERR_INVALID, "unknown dtype %d", dtype);
+    if (nrows < 0 || ncols <= 0) return fail(LO_ERR_INVALID, "bad shape %lld x %d", (long long)nrows, ncols);
+    if (!base_dev && nrows > 0) return fail(LO_ERR_INVALID, "base_dev is NULL");
+    if (pitch_bytes < (int64_t)((size_t)nrows * es))
+        return fail(LO_ERR_INVALID, "pitch %lld smaller than a column (%lld bytes)", (long long)pitch_bytes,
+                    (long long)((size_t)nrows * es));
+    if ((uintptr_t)base_dev % es || pitch_bytes % (int64_t)es)
+        return fail(LO_ERR_ALIGNMENT, "base / pitch not aligned to the element size %zu", es);
+    lo_table *t = new (std::nothrow) lo_table;
+    if (!t) return fail(LO_ERR_NOMEM, "out of host memory");
+    t->dtype = dtype; t->nrows = nrows; t->ncols = ncols; t->pitch = pitch_bytes;
+    t->base = (char *)base_dev; t->owned = false; t->device = ctx->device;
+    *out = t;
+    return LO_OK;
+}
+
+int lo_table_free(lo_ctx *ctx, lo_table *t) {
+    LO_TRY(check_ctx(ctx));
+    if (!t) return LO_OK;
+    if (t->owned && t->base) LO_CUDA(cudaFree(t->base));
+    delete t;
+    return LO_OK;
+}
+
+int lo_table_info(const lo_table *t, int *dtype, int64_t *nrows, int32_t *ncols, int64_t *pitch_bytes,
+                  void **base_dev) {
+    if (!t) return fail(LO_ERR_INVALID, "table is NULL");
+    if (dtype) *dtype = t->dtype;
+    if (nrows) *nrows = t->nrows;
+    if (ncols) *ncols = t->ncols;
+    if (pitch_bytes) *pitch_bytes = t->pitch;
+    if (base_dev) *base_dev = t->base;
+    return LO_OK;
+}
+
+static int check_range(const lo_table *t, int32_t col, int64_t row0, int64_t nrows) {
+    if (!t) return fail(LO_ERR_INVALID, "table is NULL");
+    if (col < 0 || col >= t->ncols) return fail(LO_ERR_INVALID, "column %d outside [0, %d)", col, t->ncols);
+    if (row0 < 0 || nrows < 0 || row0 + nrows > t->nrows)
+        return fail(LO_ERR_INVALID, "rows [%lld, %lld) outside [0, %lld)", (long long)row0,
+                    (long long)(row0 + nrows), (long long)t->nrows);
+    return LO_OK;
+}
+
+int lo_table_upload_col(lo_ctx *ctx, lo_table *t, int32_t col, int64_t row0, const void *host, int64_t nrows) {
+    LO_TRY(check_ctx(ctx));
+    LO_TRY(check_range(t, col, row0, nrows));
+    if (nrows == 0) return LO_OK;
+    if (!host) return fail(LO_ERR_INVALID, "host is NULL");
+    const size_t es = dtype_size(t->dtype);
+    LO_CUDA(cudaMemcpy(t->base + (int64_t)col * t->pitch + row0 * (int64_t)es, host, (size_t)nrows * es,
+                       cudaMemcpyHostToDevice));
+    return LO_OK;
+}
+
+int lo_table_download_col(lo_ctx *ctx, const lo_table *t, int32_t col, int64_t row0, void *host, int64_t nrows) {
+    LO_TRY(check_ctx(ctx));
+    LO_TRY(check_range(t, col, row0, nrows));
+    if (nrows == 0) return LO_OK;
+    if (!host) return fail(LO_ERR_INVALID, "host is NULL");
+    const size_t es = dtype_size(t->dtype);
+    LO_CUDA(cudaDeviceSynchronize());
+    LO_CUDA(cudaMemcpy(host, t->base + (int64_t)col * t->pitch + row0 * (int64_t)es, (size_t)nrows * es,
+                       cudaMemcpyDeviceToHost));
+    return LO_OK;
+}
+
+int lo_table_fill_synthetic_dev(lo_ctx *ctx, lo_table *t, int kind, uint64_t seed, int64_t row_offset,
+                                double lo_v, double hi_v, void *stream) {
+    LO_TRY(check_ctx(ctx));
+    if (!t) return fail(LO_ERR_INVALID, "table is NULL");
+    if (t->nrows == 0) return LO_OK;
+    cudaStream_t s = pick(ctx, stream);
+    const int grid = ctx->sm_count * 8;
+    if (kind == LO_SYNTH_MNIST_U8) {
+        if (t->dtype != LO_U8) return fail(LO_ERR_INVALID, "LO_SYNTH_MNIST_U8 needs an LO_U8 table");
+        lo::k_fill_u8_mnist<<<grid, 256, 0, s>>>((uint8_t *)t->base, t->pitch, t->nrows, t->ncols, seed, row_offset);
+    } else if (kind >= LO_SYNTH_UNIFORM && kind <= LO_SYNTH_CONSTCOL) {
+        if (t->dtype != LO_F64) return fail(LO_ERR_INVALID, "f64 generators need an LO_F64 table");
+        if (!(hi_v > lo_v) || !std::isfinite(lo_v) || !std::isfinite(hi_v) || hi_v == 0.0)
+            return fail(LO_ERR_INVALID, "generator range must be finite with hi > lo and hi != 0");
+        lo::k_fill_f64<<<grid, 256, 0, s>>>((double *)t->base, t->pitch / 8, t->nrows, t->ncols, kind, seed,
+                                            row_offset, lo_v, hi_v);
+    } else {
+        return fail(LO_ERR_INVALID, "unknown generator kind %d", kind);
+    }
+    LO_CUDA(cudaGetLastError());
+    ctx->launches.fetch_add(1, std::memory_order_relaxed);
+    return LO_OK;
+}
+
+int lo_table_checksum(lo_ctx *ctx, const lo_table *t, int32_t col, int64_t row_offset, uint64_t *out) {
+    LO_TRY(check_ctx(ctx));
+    LO_TRY(check_range(t, col, 0, 0));
+    if (!out) return fail(LO_ERR_INVALID, "out is NULL");
+    unsigned long long *d = nullptr;
+    LO_CUDA(cudaMalloc((void **)&d, 8));
+    cudaStream_t s = ctx->stream;
+    cudaError_t e = cudaMemsetAsync(d, 0, 8, s);
+    if (e == cudaSuccess && t->nrows > 0) {
+        const char *p = t->base + (int64_t)col * t->pitch;
+        const int grid = ctx->sm_count * 8;
+        if (t->dtype == LO_F64)      lo::k_checksum<double><<<grid, 256, 0, s>>>((const double *)p, t->nrows, row_offset, d);
+        else if (t->dtype == LO_F32) lo::k_checksum<float><<<grid, 256, 0, s>>>((const float *)p, t->nrows, row_offset, d);
+        else                         lo::k_checksum<uint8_t><<<grid, 256, 0, s>>>((const uint8_t *)p, t->nrows, row_offset, d);
+        e = cudaGetLastError();
+        ctx->launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    unsigned long long h = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(LO_ERR_CUDA, "checksum: %s", cudaGetErrorString(e));
+    *out = h;
+    return LO_OK;
+}
+
+// ---- hot path, device resident ------------------------------------------------------------------
+int lo_project_cast_dev(lo_ctx *ctx, const lo_table *in, const int32_t *col_idx, int32_t k, lo_table *out,
+                        void *stream) {
+    LO_TRY(check_ctx(ctx));
+    if (!out) return fail(LO_ERR_INVALID, "output table is NULL");
+    return project_cast_hist_impl(ctx, in, col_idx, k, out, nullptr, nullptr, pick(ctx, stream));
+}
+
+int lo_project_cast_hist_dev(lo_ctx *ctx, const lo_table *in, const int32_t *col_idx, int32_t k, lo_table *out,
+                             const lo_hist_spec *spec, uint64_t *counts_dev, void *stream) {
+    LO_TRY(check_ctx(ctx));
+    if (!spec) return fail(LO_ERR_INVALID, "spec is NULL (use lo_project_cast_dev for projection only)");
+    return project_cast_hist_impl(ctx, in, col_idx, k, out, spec, counts_dev, pick(ctx, stream));
+}
+
+int lo_hist_u8_cols_dev(lo_ctx *ctx, const lo_table *in, const int32_t *col_idx, int32_t k, uint64_t *counts_dev,
+                        void *stream) {
+    LO_TRY(check_ctx(ctx));
+    return hist_u8_impl(ctx, in, col_idx, k, counts_dev, pick(ctx, stream));
+}
+
+int lo_counts_alloc(lo_ctx *ctx, int64_t n, uint64_t **out_dev) {
+    LO_TRY(check_ctx(ctx));
+    if (!out_dev || n <= 0) return fail(LO_ERR_INVALID, "bad arguments");
+    LO_CUDA(cudaMalloc((void **)out_dev, (size_t)n * 8));
+    LO_CUDA(cudaMemset(*out_dev, 0, (size_t)n * 8));
+    return LO_OK;
+}
+
+int lo_counts_free(lo_ctx *ctx, uint64_t *counts_dev) {
+    LO_TRY(check_ctx(ctx));
+    if (counts_dev) LO_CUDA(cudaFree(counts_dev));
+    return LO_OK;
+}
+
+int lo_counts_zero_dev(lo_ctx *ctx, uint64_t *counts_dev, int64_t n, void *stream) {
+    LO_TRY(check_ctx(ctx));
+    if (!counts_dev || n <= 0) return fail(LO_ERR_INVALID, "bad arguments");
+    LO_CUDA(cudaMemsetAsync(counts_dev, 0, (size_t)n * 8, pick(ctx, stream)));
+    return LO_OK;
+}
+
+int lo_counts_download(lo_ctx *ctx, const uint64_t *counts_dev, int64_t n, uint64_t *host, void *stream) {
+    LO_TRY(check_ctx(ctx));
+    if (!counts_dev || !host || n <= 0) return fail(LO_ERR_INVALID, "bad arguments");
+    cudaStream_t s = pick(ctx, stream);
+    LO_CUDA(cudaMemcpyAsync(host, counts_dev, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
+    LO_CUDA(cudaStreamSynchronize(s));
+    return LO_OK;
+}
+
+// ---- hot path, host buffers ---------------------------------------------------------------------
+// Three-stream pipeline over row chunks; chunk c uses staging slot c & 1:
+//   h2d stream : wait(kernel of chunk c-2 done)  -> k column copies          -> ev_h2d[slot]
+//   compute    : wait(ev_h2d[slot]), wait(d2h of chunk c-2 done) -> kernel   -> ev_k[slot]
+//   d2h stream : wait(ev_k[slot]) -> k column copies back                    -> ev_d2h[slot]
+int lo_project_cast_hist_host(lo_ctx *ctx, const double *const *in_cols, int64_t nrows, int32_t k,
+                              float *const *out_cols, const lo_hist_spec *spec, uint64_t *counts,
+                              lo_host_timing *timing) {
+    LO_TRY(check_ctx(ctx));
+    if (k <= 0) return fail(LO_ERR_INVALID, "k must be > 0 (got %d)", k);
+    if (nrows < 0) return fail(LO_ERR_INVALID, "nrows < 0");
+    if (!in_cols) return fail(LO_ERR_INVALID, "in_cols is NULL");
+    if (!out_cols && !spec) return fail(LO_ERR_INVALID, "nothing to do: no out_cols and no spec");
+    if (spec && !counts) return fail(LO_ERR_INVALID, "counts is NULL");
+    for (int j = 0; j < k; ++j) {
+        if (nrows > 0 && !in_cols[j]) return fail(LO_ERR_INVALID, "in_cols[%d] is NULL", j);
+        if (nrows > 0 && out_cols && !out_cols[j]) return fail(LO_ERR_INVALID, "out_cols[%d] is NULL", j);
+    }
+    std::vector<float> w(k);
+    if (spec) LO_TRY(check_spec(spec, k, w.data()));
+    const auto t0 = std::chrono::steady_clock::now();
+    const int64_t launches0 = ctx->launches.load();
+    const size_t ncounts = spec ? (size_t)k * (size_t)spec->nbins : 0;
+    if (spec) memset(counts, 0, ncounts * 8);
+    double h2d = 0, d2h = 0;
+    if (nrows > 0) {
+        std::lock_guard<std::mutex> lk(ctx->host_mu);
+        const int64_t crows = chunk_rows_for(nrows, k, 8, lo::kTileRows);
+        const int64_t in_pitch = crows * 8, out_pitch = crows * 4;   // multiples of 256
+        LO_TRY(ensure_stage(ctx, (size_t)in_pitch * k, out_cols ? (size_t)out_pitch * k : 0, ncounts));
+        if (spec) LO_CUDA(cudaMemsetAsync(ctx->host_counts_dev, 0, ncounts * 8, ctx->stream));
+        std::vector<int32_t> ident(k);
+        for (int j = 0; j < k; ++j) ident[j] = j;
+        const int64_t nchunks = (nrows + crows - 1) / crows;
+        for (int64_t c = 0; c < nchunks; ++c) {
+            const int slot = (int)(c & 1);
+            const int64_t r0 = c * crows, n = std::min(crows, nrows - r0);
+            if (c >= 2) LO_CUDA(cudaStreamWaitEvent(ctx->h2d, ctx->ev_k[slot], 0));
+            for (int j = 0; j < k; ++j)
+                LO_CUDA(cudaMemcpyAsync(ctx->stage_in[slot] + (int64_t)j * in_pitch, in_cols[j] + r0, (size_t)n * 8,
+                                        cudaMemcpyHostToDevice, ctx->h2d));
+            h2d += (double)n * 8 * k;
+            LO_CUDA(cudaEventRecord(ctx->ev_h2d[slot], ctx->h2d));
+            LO_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[slot], 0));
+            if (c >= 2 && out_cols) LO_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[slot], 0));
+            lo_table tin  = {LO_F64, n, k, in_pitch, ctx->stage_in[slot], false, ctx->device};
+            lo_table tout = {LO_F32, n, k, out_pitch, out_cols ? ctx->stage_out[slot] : nullptr, false, ctx->device};
+            LO_TRY(project_cast_hist_impl(ctx, &tin, ident.data(), k, out_cols ? &tout : nullptr, spec,
+                                          (uint64_t *)ctx->host_counts_dev, ctx->stream));
+            LO_CUDA(cudaEventRecord(ctx->ev_k[slot], ctx->stream));
+            if (out_cols) {
+                LO_CUDA(cudaStreamWaitEvent(ctx->d2h, ctx->ev_k[slot], 0));
+                for (int j = 0; j < k; ++j)
+                    LO_CUDA(cudaMemcpyAsync(out_cols[j] + r0, ctx->stage_out[slot] + (int64_t)j * out_pitch,
+                                            (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->d2h));
+                d2h += (double)n * 4 * k;
+                LO_CUDA(cudaEventRecord(ctx->ev_d2h[slot], ctx->d2h));
+            }
+        }
+        if (spec) {
+            LO_CUDA(cudaMemcpyAsync(counts, ctx->host_counts_dev, ncounts * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            d2h += (double)ncounts * 8;
+        }
+        LO_CUDA(cudaStreamSynchronize(ctx->stream));
+        LO_CUDA(cudaStreamSynchronize(ctx->d2h));
+        LO_CUDA(cudaStreamSynchronize(ctx->h2d));
+    }
+    if (timing) {
+        timing->total_ms  = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        timing->h2d_bytes = h2d;
+        timing->d2h_bytes = d2h;
+        timing->launches  = ctx->launches.load() - launches0;
+    }
+    return LO_OK;
+}
+
+int lo_hist_u8_cols_host(lo_ctx *ctx, const uint8_t *const *in_cols, int64_t nrows, int32_t k, uint64_t *counts,
+                         lo_host_timing *timing) {
+    LO_TRY(check_ctx(ctx));
+    if (k <= 0) return fail(LO_ERR_INVALID, "k must be > 0 (got %d)", k);
+    if (nrows < 0) return fail(LO_ERR_INVALID, "nrows < 0");
+    if (!in_cols || !counts) return fail(LO_ERR_INVALID, "NULL argument");
+    for (int j = 0; j < k; ++j)
+        if (nrows > 0 && !in_cols[j]) return fail(LO_ERR_INVALID, "in_cols[%d] is NULL", j);
+    const auto t0 = std::chrono::steady_clock::now();
+    const int64_t launches0 = ctx->launches.load();
+    const size_t ncounts = (size_t)k * 256;
+    memset(counts, 0, ncounts * 8);
+    double h2d = 0, d2h = 0;
+    if (nrows > 0) {
+        std::lock_guard<std::mutex> lk(ctx->host_mu);
+        const int64_t crows = chunk_rows_for(nrows, k, 1, lo::kU8TileRows);
+        const int64_t pitch = crows;   // multiple of 61440 -> multiple of 256
+        LO_TRY(ensure_stage(ctx, (size_t)pitch * k, 0, ncounts));
+        LO_CUDA(cudaMemsetAsync(ctx->host_counts_dev, 0, ncounts * 8, ctx->stream));
+        std::vector<int32_t> ident(k);
+        for (int j = 0; j < k; ++j) ident[j] = j;
+        const int64_t nchunks = (nrows + crows - 1) / crows;
+        for (int64_t c = 0; c < nchunks; ++c) {
+            const int slot = (int)(c & 1);
+            const int64_t r0 = c * crows, n = std::min(crows, nrows - r0);
+            if (c >= 2) LO_CUDA(cudaStreamWaitEvent(ctx->h2d, ctx->ev_k[slot], 0));
+            for (int j = 0; j < k; ++j)
+                LO_CUDA(cudaMemcpyAsync(ctx->stage_in[slot] + (int64_t)j * pitch, in_cols[j] + r0, (size_t)n,
+                                        cudaMemcpyHostToDevice, ctx->h2d));
+            h2d += (double)n * k;
+            LO_CUDA(cudaEventRecord(ctx->ev_h2d[slot], ctx->h2d));
+            LO_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[slot], 0));
+            lo_table tin = {LO_U8, n, k, pitch, ctx->stage_in[slot], false, ctx->device};
+            LO_TRY(hist_u8_impl(ctx, &tin, ident.data(), k, (uint64_t *)ctx->host_counts_dev, ctx->stream));
+            LO_CUDA(cudaEventRecord(ctx->ev_k[slot], ctx->stream));
+        }
+        LO_CUDA(cudaMemcpyAsync(counts, ctx->host_counts_dev, ncounts * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        d2h += (double)ncounts * 8;
+        LO_CUDA(cudaStreamSynchronize(ctx->stream));
+        LO_CUDA(cudaStreamSynchronize(ctx->h2d));
+    }
+    if (timing) {
+        timing->total_ms  = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        timing->h2d_bytes = h2d;
+        timing->d2h_bytes = d2h;
+        timing->launches  = ctx->launches.load() - launches0;
+    }
+    return LO_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,205 @@
+"""GPU parity: libloexec (through the C ABI) vs the CPU oracle, bit for bit.
+
+Sizes here are ones the oracle finishes in seconds; full BASELINE.json sizes are covered in
+test_gpu_fullsize.py through the streaming oracle and size-independent properties.
+"""
+import numpy as np
+import pytest
+
+from oracle import bsem_numpy as bn
+from oracle import cport
+
+pytestmark = pytest.mark.gpu
+
+SEED = 20260921
+TILE = 61440
+
+
+def _bits(a):
+    return a.view({4: np.uint32, 8: np.uint64, 1: np.uint8}[a.dtype.itemsize])
+
+
+def _check_project_cast_hist(engine, table_np, col_idx, nbins, lo, hi, with_out=True, out_dtype="f32"):
+    t = engine.table_from_numpy(table_np)
+    k = len(col_idx)
+    out = engine.table(out_dtype, t.nrows, k) if with_out else None
+    counts = engine.project_cast_hist(t, col_idx, nbins, lo, hi, out=out).to_numpy()
+    exp_out, exp_counts = bn.project_cast_hist(table_np, col_idx, nbins, np.broadcast_to(np.float32(lo), (k,)),
+                                               np.broadcast_to(np.float32(hi), (k,)))
+    assert counts.dtype == np.uint64 and counts.shape == (k, nbins)
+    np.testing.assert_array_equal(counts, exp_counts)
+    if with_out:
+        for j in range(k):
+            got = out.to_numpy(j)
+            if out_dtype == "f32":
+                np.testing.assert_array_equal(_bits(got), _bits(exp_out[j]))
+            else:
+                np.testing.assert_array_equal(_bits(got), _bits(np.ascontiguousarray(table_np[col_idx[j]])))
+        out.free()
+    t.free()
+    return counts
+
+
+@pytest.mark.parametrize("nrows", [1, 3, 4, 5, 255, 1024, 4099, TILE - 1, TILE, TILE + 1, 3 * TILE + 17])
+def test_project_cast_hist_ragged_sizes(engine, nrows):
+    table = bn.synth_table_f64(1, SEED, 5, 0, nrows)
+    _check_project_cast_hist(engine, table, [4, 0, 2], 256, -1000.0, 1000.0)
+
+
+@pytest.mark.parametrize("nbins", [1, 2, 3, 4, 5, 10, 64, 100, 255, 256])
+def test_nbins(engine, nbins):
+    table = bn.synth_table_f64(1, SEED + 1, 3, 1000, 200_000)
+    _check_project_cast_hist(engine, table, [0, 1, 2], nbins, -1000.0, 1000.0)
+
+
+def test_special_values_and_per_column_ranges(engine):
+    nrows = 300_000
+    table = bn.synth_table_f64(1, SEED + 2, 8, 0, nrows)
+    lo = np.array([-1000, -500, 0, -1, -1e30, 1, -0.0, 999], dtype=np.float32)
+    hi = np.array([1000, 500, 1000, 1, 1e30, 2, 1e-38, 1000], dtype=np.float32)
+    c = _check_project_cast_hist(engine, table, list(range(8)), 256, lo, hi)
+    assert c.sum() > 0
+
+
+def test_constant_column_contention(engine):
+    table = bn.synth_table_f64(2, SEED, 4, 0, 500_000)
+    c = _check_project_cast_hist(engine, table, [0, 1, 0, 3], 256, -1000.0, 1000.0)
+    assert c[0].max() >= 500_000 - 600      # one hot bin (minus the special-value rows)
+
+
+def test_histogram_only_and_f64_copy(engine):
+    table = bn.synth_table_f64(1, SEED + 3, 6, 77, 150_001)
+    _check_project_cast_hist(engine, table, [5, 1], 10, -1000.0, 1000.0, with_out=False)
+    _check_project_cast_hist(engine, table, [5, 1, 3], 16, -250.0, 750.0, out_dtype="f64")
+
+
+def test_projection_cast_only_matches_c_oracle(engine):
+    nrows = 1_000_003
+    table = bn.synth_table_f64(1, SEED, 16, 0, nrows)
+    perm = [3, 15, 0, 7, 7, 12]
+    t = engine.table_from_numpy(table)
+    out = engine.project_cast(t, perm)
+    for j, c in enumerate(perm):
+        exp = cport.cast_f64_f32(table[c])
+        np.testing.assert_array_equal(_bits(out.to_numpy(j)), _bits(exp))
+        assert out.checksum(j, 5) == cport.checksum(exp, 5) == bn.checksum(exp, 5)
+    out.free(); t.free()
+
+
+def test_known_answer_casts(engine):
+    # SURVEY.md §8c known answers for fp64 -> fp32 RNE
+    x = np.array([0.1, 16777217.0, 1e39, -1e-46, 3.4028235677973366e38, 1e-40, -0.0, np.nan, 1 + 2.0 ** -24],
+                 dtype=np.float64)
+    want = np.array([0x3DCCCCCD, 0x4B800000, 0x7F800000, 0x80000000, 0x7F800000, 0x000116C2, 0x80000000, 0x7FC00000,
+                     0x3F800000], dtype=np.uint32)
+    t = engine.table_from_numpy(x[None, :])
+    out = engine.project_cast(t, [0])
+    np.testing.assert_array_equal(_bits(out.to_numpy(0)), want)
+    out.free(); t.free()
+
+
+def test_counts_accumulate_over_row_shards(engine):
+    # linearity: histogram of the whole == sum of histograms of row shards accumulated in one buffer
+    nrows = 400_000
+    table = bn.synth_table_f64(1, SEED + 4, 4, 0, nrows)
+    whole = _check_project_cast_hist(engine, table, [0, 1, 2, 3], 256, -1000.0, 1000.0, with_out=False)
+    acc = engine.counts(4, 256)
+    for r0, r1 in [(0, 100_001), (100_001, 100_002), (100_002, 399_999), (399_999, nrows)]:
+        t = engine.table_from_numpy(table[:, r0:r1])
+        engine.project_cast_hist(t, [0, 1, 2, 3], 256, -1000.0, 1000.0, counts=acc)
+        t.free()
+    np.testing.assert_array_equal(acc.to_numpy(), whole)
+    acc.free()
+
+
+def test_device_generator_matches_oracle(engine):
+    for kind in (0, 1, 2):
+        t = engine.table("f64", 70_001, 5).fill_synthetic(kind, SEED, row_offset=123_456_789)
+        for c in range(5):
+            exp = cport.synth_f64(kind, SEED, c, 123_456_789, 70_001)
+            np.testing.assert_array_equal(_bits(t.to_numpy(c)), _bits(exp))
+        t.free()
+    t = engine.table("u8", 100_003, 150).fill_synthetic(3, SEED, row_offset=99)
+    for c in (0, 4 * 28 + 4, 39, 149):
+        np.testing.assert_array_equal(t.to_numpy(c), cport.synth_u8(SEED, c, 99, 100_003))
+    t.free()
+
+
+@pytest.mark.parametrize("nrows", [1, 15, 16, 17, 4097, TILE - 3, TILE, 2 * TILE + 5])
+def test_hist_u8_cols(engine, nrows):
+    ncols = 784 if nrows <= 4097 else 150
+    table = bn.synth_table_u8(SEED, ncols, 0, nrows)
+    t = engine.table_from_numpy(table)
+    cols = list(range(ncols))[::-1]
+    got = engine.hist_u8_cols(t, cols).to_numpy()
+    np.testing.assert_array_equal(got, bn.hist_u8_cols(table, cols))
+    assert (got.sum(axis=1) == nrows).all()
+    t.free()
+
+
+def test_hist_u8_all_values_and_constant(engine):
+    rng = np.random.default_rng(5)
+    table = np.stack([rng.integers(0, 256, 300_000, dtype=np.uint8), np.full(300_000, 255, np.uint8),
+                      np.arange(300_000, dtype=np.uint64).astype(np.uint8)])
+    t = engine.table_from_numpy(table)
+    got = engine.hist_u8_cols(t, [0, 1, 2]).to_numpy()
+    np.testing.assert_array_equal(got, cport.hist_u8_cols(list(table)))
+    t.free()
+
+
+def test_unaligned_wrapped_tables(engine):
+    # foreign device memory with an odd element offset / pitch takes the scalar kernel variant
+    nrows, ncols = 100_003, 3
+    table = bn.synth_table_f64(1, SEED, ncols, 0, nrows)
+    big = engine.table("f64", (nrows + 1) * ncols + 8, 1)
+    flat = np.zeros((nrows + 1) * ncols + 8)
+    for c in range(ncols):
+        flat[1 + c * (nrows + 1): 1 + c * (nrows + 1) + nrows] = table[c]
+    big.upload(0, flat)
+    view = engine.wrap("f64", nrows, ncols, big.base_ptr + 8, (nrows + 1) * 8)
+    out = engine.table("f32", nrows, ncols)
+    counts = engine.project_cast_hist(view, [2, 0, 1], 256, -1000.0, 1000.0, out=out).to_numpy()
+    exp_out, exp_counts = bn.project_cast_hist(table, [2, 0, 1], 256, [-1000.0] * 3, [1000.0] * 3)
+    np.testing.assert_array_equal(counts, exp_counts)
+    for j in range(3):
+        np.testing.assert_array_equal(_bits(out.to_numpy(j)), _bits(exp_out[j]))
+    view.free(); out.free(); big.free()
+
+
+def test_host_buffer_entry_points(engine):
+    nrows, k = 1_500_007, 6
+    table = bn.synth_table_f64(1, SEED + 9, k, 0, nrows)
+    cols = [np.ascontiguousarray(table[j]) for j in range(k)]
+    outs = [np.empty(nrows, dtype=np.float32) for _ in range(k)]
+    lo = np.linspace(-1000, -900, k).astype(np.float32)
+    hi = np.linspace(900, 1000, k).astype(np.float32)
+    counts, timing = engine.project_cast_hist_host(cols, 256, lo, hi, out=outs)
+    exp_out, exp_counts = bn.project_cast_hist(table, range(k), 256, lo, hi)
+    np.testing.assert_array_equal(counts, exp_counts)
+    for j in range(k):
+        np.testing.assert_array_equal(_bits(outs[j]), _bits(exp_out[j]))
+    assert timing["h2d_bytes"] == nrows * k * 8 and timing["launches"] >= 1
+    # pinned buffers, histogram only
+    pin = engine.pinned_empty((k, nrows), np.float64)
+    pin[:] = table
+    counts2, _ = engine.project_cast_hist_host([pin[j] for j in range(k)], 256, lo, hi)
+    np.testing.assert_array_equal(counts2, exp_counts)
+    # bytes
+    tb = bn.synth_table_u8(SEED, 30, 0, 200_001)
+    c8, _ = engine.hist_u8_cols_host([np.ascontiguousarray(tb[j]) for j in range(30)])
+    np.testing.assert_array_equal(c8, bn.hist_u8_cols(tb, range(30)))
+
+
+def test_error_reporting(engine):
+    from learningorchestra_b200._native import LoexecError, LO_ERR_INVALID
+    t = engine.table("f64", 100, 2)
+    with pytest.raises(LoexecError) as e:
+        engine.project_cast_hist(t, [0, 2], 256, -1.0, 1.0)
+    assert e.value.code == LO_ERR_INVALID and "col_idx" in e.value.message
+    with pytest.raises(LoexecError):
+        engine.project_cast_hist(t, [0], 257, -1.0, 1.0)
+    with pytest.raises(LoexecError):
+        engine.project_cast_hist(t, [0], 10, 1.0, 1.0)
+    with pytest.raises(LoexecError):
+        engine.hist_u8_cols(t, [0])
+    t.free()
