@@ -125,6 +125,14 @@ int lo_table_fill_synthetic_dev(lo_ctx *ctx, lo_table *t, int kind, uint64_t see
 int lo_table_checksum(lo_ctx *ctx, const lo_table *t, int32_t col, int64_t row_offset,
                       uint64_t *out);
 
+/* Exhaustive self-test of the binning arithmetic for one (lo, hi, nbins): runs all 2^32 fp32 bit
+ * patterns through the branch-free divide the fast kernels use AND through the IEEE divide, and
+ * returns how many bin indices differ (must be 0 whenever *fast_path_used == 1, i.e. whenever the
+ * library would pick the fast kernels for this range; ranges that fail the safety conditions run
+ * the IEEE-divide kernels instead). */
+int lo_selftest_fastdiv(lo_ctx *ctx, float lo, float hi, int32_t nbins, int *fast_path_used,
+                        uint64_t *mismatches);
+
 /* ---- the hot path, device-resident ------------------------------------------------------ */
 /* out[j][r] = cast(in[col_idx[j]][r]) for j < k.  in: LO_F64.  out: LO_F32 (fp64->fp32 RNE,
  * NaN -> 0x7fc00000) or LO_F64 (plain copy).  out->ncols >= k, out->nrows == in->nrows. */

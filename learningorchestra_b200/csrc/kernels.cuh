@@ -32,6 +32,22 @@ constexpr int kTileRows     = kThreads * kElemsPerThread;  // 61440 rows per til
 constexpr int kHistRows     = 64;                  // smem words per thread (256 bins / 4)
 constexpr int kHistSmemBytes = (kHistRows * kThreads + 256) * 4;   // 66560 B -> 3 CTAs / SM
 
+// software pipeline of the full-tile path: kPfBuf register buffers of kPfBatch 32-byte vectors;
+// kPfBuf-1 batches are always in flight per thread while one is being converted / binned
+#ifndef LO_PF_BATCH
+#define LO_PF_BATCH 5
+#endif
+#ifndef LO_PF_NBUF
+#define LO_PF_NBUF 2
+#endif
+#ifndef LO_MIN_CTAS
+#define LO_MIN_CTAS 2
+#endif
+constexpr int kPfBatch   = LO_PF_BATCH;
+constexpr int kPfBuf     = LO_PF_NBUF;
+constexpr int kPfBatches = kVecPerThread / kPfBatch;
+static_assert(kVecPerThread % kPfBatch == 0 && kPfBatches % kPfBuf == 0, "pipeline shape must tile the 60 vectors");
+
 constexpr int kU8VecBytes   = 16;
 constexpr int kU8Batch      = 5;
 constexpr int kU8Batches    = 3;
@@ -106,13 +122,66 @@ __device__ __forceinline__ void bump(uint8_t *priv /* smem + 4*tid */, uint32_t 
 }
 
 // fixed-width binning of the CAST value: fp32 RN subtract, fp32 RN divide,
-// truncate, close the last bin.  NaN and out-of-range values are skipped.
-__device__ __forceinline__ void bin_f32(uint8_t *priv, float f, float lo, float hi, float w, int last) {
-    if (f >= lo && f <= hi) {
-        float t = __fdiv_rn(__fsub_rn(f, lo), w);
-        int   i = __float2int_rz(t);
-        bump(priv, (uint32_t)min(i, last));
+// truncate, close the last bin.  NaN and out-of-range values are skipped (bin index < 0).
+//
+// FASTDIV = false: the divide is the compiler's IEEE __fdiv_rn (MUFU.RCP + Newton + FCHK slow path).
+// FASTDIV = true : the same correctly-rounded quotient without the XU op and without the branch,
+//   using the reciprocal r = RN(1/w) computed once per CTA:
+//       q0 = RN(d*r); q1 = RN(q0 + (d - w*q0)*r); q2 = RN(q1 + (d - w*q1)*r)      (remainders exact in FMA)
+//   q2 == RN(d/w) whenever d >= w/2 (Markstein's theorem; the one exception, a divisor whose
+//   significand is all ones, and exponents that could under/overflow an intermediate are excluded by
+//   the host, which then launches the FASTDIV = false variant — see fastdiv_ok() in loexec.cu and
+//   DESIGN.md §3.3).  For d < w/2 every q stays below 1, so the truncated bin is 0 either way.
+//   The truncation is an FADD.RZ against 2^23 (integer part lands in the low significand bits)
+//   instead of an F2I, which would be another XU-pipe op.
+struct BinParams {
+    float lo, hi, w, r;
+    int   last;
+};
+
+template <bool FASTDIV>
+__device__ __forceinline__ int bin_index_f32(float f, const BinParams &B) {
+    if (!(f >= B.lo && f <= B.hi)) return -1;
+    const float d = __fsub_rn(f, B.lo);
+    int i;
+    if (FASTDIV) {
+        float q = __fmul_rn(d, B.r);
+        q = __fmaf_rn(__fmaf_rn(-B.w, q, d), B.r, q);
+        q = __fmaf_rn(__fmaf_rn(-B.w, q, d), B.r, q);
+        i = __float_as_int(__fadd_rz(q, 8388608.0f)) - 0x4B000000;   // trunc(q), 0 <= q < 2^23
+    } else {
+        i = __float2int_rz(__fdiv_rn(d, B.w));
     }
+    return min(i, B.last);
+}
+
+template <bool FASTDIV>
+__device__ __forceinline__ void bin_f32(uint8_t *priv, float f, const BinParams &B) {
+    int i = bin_index_f32<FASTDIV>(f, B);
+    if (i >= 0) bump(priv, (uint32_t)i);
+}
+
+// Four increments with their shared-memory latencies overlapped: all four counters are read
+// before any is written, so equal bins must be merged by hand — element i adds 1 + (number of
+// earlier elements in the same bin) and the stores go out in order, the last one carrying the
+// total.  Skipped elements (bin < 0) never compare equal to a valid bin and touch no memory.
+__device__ __forceinline__ void bump4(uint8_t *priv, int b0, int b1, int b2, int b3) {
+    uint8_t *p0 = priv + bin_byte_offset((uint32_t)b0), *p1 = priv + bin_byte_offset((uint32_t)b1);
+    uint8_t *p2 = priv + bin_byte_offset((uint32_t)b2), *p3 = priv + bin_byte_offset((uint32_t)b3);
+    const bool v0 = b0 >= 0, v1 = b1 >= 0, v2 = b2 >= 0, v3 = b3 >= 0;
+    uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+    if (v0) c0 = *p0;
+    if (v1) c1 = *p1;
+    if (v2) c2 = *p2;
+    if (v3) c3 = *p3;
+    c0 += 1;
+    c1 += 1 + (b1 == b0);
+    c2 += 1 + (b2 == b0) + (b2 == b1);
+    c3 += 1 + (b3 == b0) + (b3 == b1) + (b3 == b2);
+    if (v0) *p0 = (uint8_t)c0;
+    if (v1) *p1 = (uint8_t)c1;
+    if (v2) *p2 = (uint8_t)c2;
+    if (v3) *p3 = (uint8_t)c3;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -164,8 +233,8 @@ __device__ __forceinline__ void fold_and_flush(uint32_t *smem, int rows, int nbi
 //   ALIGNED: column slabs (in and out) are 32-byte aligned -> 256-bit loads, 128/256-bit stores
 // grid.x = k * tiles_per_col ; tile index fastest along rows
 // ---------------------------------------------------------------------------------------------
-template <int OUT, bool HIST, bool ALIGNED>
-__global__ void __launch_bounds__(kThreads, 3)
+template <int OUT, bool HIST, bool ALIGNED, bool FASTDIV>
+__global__ void __launch_bounds__(kThreads, LO_MIN_CTAS)
 k_project_cast_hist(const char *__restrict__ in_base, long long in_pitch,
                     char *__restrict__ out_base, long long out_pitch,
                     long long nrows, unsigned tiles_per_col,
@@ -183,18 +252,53 @@ k_project_cast_hist(const char *__restrict__ in_base, long long in_pitch,
     if (OUT == 1) out32 = reinterpret_cast<float *>(out_base + (long long)j * out_pitch) + r0;
     if (OUT == 2) out64 = reinterpret_cast<double *>(out_base + (long long)j * out_pitch) + r0;
 
-    float lo = 0.f, hi = 0.f, w = 1.f;
-    int rows = 0, last = 0;
+    BinParams B = {0.f, 0.f, 1.f, 1.f, 0};
+    int rows = 0;
     uint8_t *priv = reinterpret_cast<uint8_t *>(smem) + 4 * threadIdx.x;
     if (HIST) {
-        lo = P.lo[j]; hi = P.hi[j]; w = P.w[j];
-        last = P.nbins - 1;
+        B.lo = P.lo[j]; B.hi = P.hi[j]; B.w = P.w[j];
+        B.r = __frcp_rn(B.w);
+        B.last = P.nbins - 1;
         rows = (P.nbins + 3) >> 2;
         zero_private(smem, rows);
         // a thread only touches its own words until fold_and_flush: no barrier needed here
     }
 
-    if (ALIGNED) {
+    if (ALIGNED && n == kTileRows) {
+        // full tile (all but the last tile of a column): no bounds checks, register-pipelined loads.
+        // vector index of (batch b, slot u) = (b*kPfBatch + u)*kThreads + tid  ->  warp-contiguous 1 KiB
+        double v[kPfBuf][kPfBatch][4];
+        const double *src = in + (long long)threadIdx.x * kVec;
+#pragma unroll
+        for (int pb = 0; pb < kPfBuf - 1; ++pb)
+#pragma unroll
+            for (int u = 0; u < kPfBatch; ++u)
+                ldg256_stream(src + (long long)(pb * kPfBatch + u) * kThreads * kVec, v[pb][u]);
+#pragma unroll 1
+        for (int b0 = 0; b0 < kPfBatches; b0 += kPfBuf) {
+#pragma unroll
+            for (int s = 0; s < kPfBuf; ++s) {
+                const int b  = b0 + s;                 // batch being processed, lives in buffer s
+                const int nb = b + kPfBuf - 1;         // batch to fetch, into buffer (s + kPfBuf - 1) % kPfBuf
+                if (nb < kPfBatches) {
+#pragma unroll
+                    for (int u = 0; u < kPfBatch; ++u)
+                        ldg256_stream(src + (long long)(nb * kPfBatch + u) * kThreads * kVec, v[(s + kPfBuf - 1) % kPfBuf][u]);
+                }
+#pragma unroll
+                for (int u = 0; u < kPfBatch; ++u) {
+                    const long long e = ((long long)(b * kPfBatch + u) * kThreads + threadIdx.x) * kVec;
+                    float f0 = cast_f64_f32(v[s][u][0]), f1 = cast_f64_f32(v[s][u][1]);
+                    float f2 = cast_f64_f32(v[s][u][2]), f3 = cast_f64_f32(v[s][u][3]);
+                    if (OUT == 1) stg128_stream(out32 + e, f0, f1, f2, f3);
+                    if (OUT == 2) stg256_stream(out64 + e, v[s][u]);
+                    if (HIST)
+                        bump4(priv, bin_index_f32<FASTDIV>(f0, B), bin_index_f32<FASTDIV>(f1, B),
+                              bin_index_f32<FASTDIV>(f2, B), bin_index_f32<FASTDIV>(f3, B));
+                }
+            }
+        }
+    } else if (ALIGNED) {
 #pragma unroll 1
         for (int b = 0; b < kBatches; ++b) {
             const long long e0 = ((long long)b * kBatch * kThreads + threadIdx.x) * kVec;   // first element of vector 0
@@ -211,10 +315,9 @@ k_project_cast_hist(const char *__restrict__ in_base, long long in_pitch,
                     float f2 = cast_f64_f32(v[u][2]), f3 = cast_f64_f32(v[u][3]);
                     if (OUT == 1) stg128_stream(out32 + e, f0, f1, f2, f3);
                     if (OUT == 2) stg256_stream(out64 + e, v[u]);
-                    if (HIST) {
-                        bin_f32(priv, f0, lo, hi, w, last); bin_f32(priv, f1, lo, hi, w, last);
-                        bin_f32(priv, f2, lo, hi, w, last); bin_f32(priv, f3, lo, hi, w, last);
-                    }
+                    if (HIST)
+                        bump4(priv, bin_index_f32<FASTDIV>(f0, B), bin_index_f32<FASTDIV>(f1, B),
+                              bin_index_f32<FASTDIV>(f2, B), bin_index_f32<FASTDIV>(f3, B));
                 }
             } else {
                 // ragged end of the column: element-wise
@@ -228,7 +331,7 @@ k_project_cast_hist(const char *__restrict__ in_base, long long in_pitch,
                             float  f = cast_f64_f32(x);
                             if (OUT == 1) out32[e + q] = f;
                             if (OUT == 2) out64[e + q] = x;
-                            if (HIST) bin_f32(priv, f, lo, hi, w, last);
+                            if (HIST) bin_f32<FASTDIV>(priv, f, B);
                         }
                     }
                 }
@@ -244,7 +347,7 @@ k_project_cast_hist(const char *__restrict__ in_base, long long in_pitch,
             float  f = cast_f64_f32(x);
             if (OUT == 1) out32[e] = f;
             if (OUT == 2) out64[e] = x;
-            if (HIST) bin_f32(priv, f, lo, hi, w, last);
+            if (HIST) bin_f32<FASTDIV>(priv, f, B);
         }
     }
 
@@ -255,8 +358,7 @@ k_project_cast_hist(const char *__restrict__ in_base, long long in_pitch,
 // K4: per-column 256-bin value counts of byte columns
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void bump_word(uint8_t *priv, uint32_t x) {
-    bump(priv, x & 0xFFu); bump(priv, (x >> 8) & 0xFFu);
-    bump(priv, (x >> 16) & 0xFFu); bump(priv, x >> 24);
+    bump4(priv, (int)(x & 0xFFu), (int)((x >> 8) & 0xFFu), (int)((x >> 16) & 0xFFu), (int)(x >> 24));
 }
 
 template <bool ALIGNED>
@@ -377,6 +479,20 @@ __global__ void k_fill_u8_mnist(uint8_t *base, long long pitch, long long nrows,
         if (py >= 4 && py < 24 && px >= 4 && px < 24 && (u & 0xFFu) >= 0x99u) v = (uint8_t)((u >> 8) & 0xFFu);
         base[(long long)c * pitch + r] = v;
     }
+}
+
+// exhaustive self-test: every one of the 2^32 fp32 bit patterns through both divide variants
+__global__ void k_selftest_fastdiv(float lo, float hi, float w, int nbins, unsigned long long *mismatches) {
+    BinParams B = {lo, hi, w, __frcp_rn(w), nbins - 1};
+    unsigned long long bad = 0;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < (1ull << 32);
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const float f = __uint_as_float((unsigned)i);
+        bad += bin_index_f32<true>(f, B) != bin_index_f32<false>(f, B);
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, s);
+    if ((threadIdx.x & 31) == 0 && bad) atomicAdd(mismatches, bad);
 }
 
 template <typename T>

@@ -133,13 +133,29 @@ int allow_smem(K kernel) {
     return LO_OK;
 }
 
+template <int OUT>
+int allow_smem_hist() {
+    LO_TRY(allow_smem(lo::k_project_cast_hist<OUT, true, true, true>));
+    LO_TRY(allow_smem(lo::k_project_cast_hist<OUT, true, true, false>));
+    LO_TRY(allow_smem(lo::k_project_cast_hist<OUT, true, false, true>));
+    LO_TRY(allow_smem(lo::k_project_cast_hist<OUT, true, false, false>));
+    return LO_OK;
+}
+
+// The branch-free divide of the FASTDIV kernels equals the IEEE quotient only under the
+// conditions of Markstein's theorem (kernels.cuh, bin_index_f32): the divisor's significand must
+// not be all ones, and w, 1/w and every quotient (<= nbins) must stay far from the exponent limits.
+bool fastdiv_ok(float w) {
+    uint32_t bits;
+    memcpy(&bits, &w, 4);
+    if ((bits & 0x007FFFFFu) == 0x007FFFFFu) return false;
+    return w >= 0x1p-100f && w <= 0x1p100f;
+}
+
 int configure_kernels() {
-    LO_TRY(allow_smem(lo::k_project_cast_hist<0, true, true>));
-    LO_TRY(allow_smem(lo::k_project_cast_hist<1, true, true>));
-    LO_TRY(allow_smem(lo::k_project_cast_hist<2, true, true>));
-    LO_TRY(allow_smem(lo::k_project_cast_hist<0, true, false>));
-    LO_TRY(allow_smem(lo::k_project_cast_hist<1, true, false>));
-    LO_TRY(allow_smem(lo::k_project_cast_hist<2, true, false>));
+    LO_TRY(allow_smem_hist<0>());
+    LO_TRY(allow_smem_hist<1>());
+    LO_TRY(allow_smem_hist<2>());
     LO_TRY(allow_smem(lo::k_hist_u8_cols<true>));
     LO_TRY(allow_smem(lo::k_hist_u8_cols<false>));
     return LO_OK;
@@ -155,12 +171,14 @@ int launch_f64(lo_ctx *ctx, const lo_table *in, const lo_table *out, int32_t out
     const size_t smem = HIST ? lo::kHistSmemBytes : 0;
     char *out_base = out ? out->base + (int64_t)out_col0 * out->pitch : nullptr;
     const long long out_pitch = out ? out->pitch : 0;
-    if (aligned)
-        lo::k_project_cast_hist<OUT, HIST, true><<<(unsigned)blocks, lo::kThreads, smem, s>>>(
-            in->base, in->pitch, out_base, out_pitch, in->nrows, tiles_per_col, counts, P);
-    else
-        lo::k_project_cast_hist<OUT, HIST, false><<<(unsigned)blocks, lo::kThreads, smem, s>>>(
-            in->base, in->pitch, out_base, out_pitch, in->nrows, tiles_per_col, counts, P);
+    bool fast = HIST;
+    for (int j = 0; HIST && j < P.k; ++j) fast = fast && fastdiv_ok(P.w[j]);
+#define LO_LAUNCH(AL, FD)                                                                              \
+    lo::k_project_cast_hist<OUT, HIST, AL, FD><<<(unsigned)blocks, lo::kThreads, smem, s>>>(           \
+        in->base, in->pitch, out_base, out_pitch, in->nrows, tiles_per_col, counts, P)
+    if (aligned) { if (fast) LO_LAUNCH(true, true); else LO_LAUNCH(true, false); }
+    else         { if (fast) LO_LAUNCH(false, true); else LO_LAUNCH(false, false); }
+#undef LO_LAUNCH
     LO_CUDA(cudaGetLastError());
     ctx->launches.fetch_add(1, std::memory_order_relaxed);
     return LO_OK;
@@ -536,6 +554,31 @@ int lo_table_checksum(lo_ctx *ctx, const lo_table *t, int32_t col, int64_t row_o
     cudaFree(d);
     if (e != cudaSuccess) return fail(LO_ERR_CUDA, "checksum: %s", cudaGetErrorString(e));
     *out = h;
+    return LO_OK;
+}
+
+int lo_selftest_fastdiv(lo_ctx *ctx, float lo_v, float hi_v, int32_t nbins, int *fast_path_used,
+                        uint64_t *mismatches) {
+    LO_TRY(check_ctx(ctx));
+    if (!mismatches) return fail(LO_ERR_INVALID, "mismatches is NULL");
+    lo_hist_spec spec = {nbins, 0, &lo_v, &hi_v};
+    float w = 0.f;
+    LO_TRY(check_spec(&spec, 1, &w));
+    if (fast_path_used) *fast_path_used = fastdiv_ok(w) ? 1 : 0;
+    unsigned long long *d = nullptr;
+    LO_CUDA(cudaMalloc((void **)&d, 8));
+    cudaError_t e = cudaMemsetAsync(d, 0, 8, ctx->stream);
+    if (e == cudaSuccess) {
+        lo::k_selftest_fastdiv<<<ctx->sm_count * 16, 256, 0, ctx->stream>>>(lo_v, hi_v, w, nbins, d);
+        e = cudaGetLastError();
+        ctx->launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    unsigned long long h = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(LO_ERR_CUDA, "selftest: %s", cudaGetErrorString(e));
+    *mismatches = h;
     return LO_OK;
 }
 

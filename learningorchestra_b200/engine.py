@@ -182,6 +182,12 @@ class Engine:
         buf = (C.c_char * max(nbytes, 1)).from_address(p.value)
         return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 
+    def selftest_fastdiv(self, lo: float, hi: float, nbins: int) -> tuple[bool, int]:
+        """(fast kernels would be used, number of fp32 bit patterns whose bin differs from IEEE division)."""
+        used, bad = C.c_int(), C.c_uint64()
+        N.check(self._lib.lo_selftest_fastdiv(self._ctx, float(lo), float(hi), int(nbins), C.byref(used), C.byref(bad)))
+        return bool(used.value), int(bad.value)
+
     # ---- hot path, device resident ---------------------------------------------------------------
     def _spec(self, k: int, nbins: int, lo, hi):
         lo_a = (C.c_float * k)(*[float(v) for v in np.broadcast_to(np.asarray(lo, dtype=np.float32), (k,))])

@@ -203,3 +203,31 @@ def test_error_reporting(engine):
     with pytest.raises(LoexecError):
         engine.hist_u8_cols(t, [0])
     t.free()
+
+
+@pytest.mark.parametrize("lo,hi,nbins", [
+    (-1000.0, 1000.0, 256), (-1000.0, 1000.0, 10), (0.0, 1.0, 256), (0.0, 255.0, 255), (-3.0, 7.0, 3),
+    (1e-30, 2e-30, 100), (-1e30, 1e30, 256), (0.1, 0.7, 7), (-123.456, 789.012, 177), (5.0, 5.000001, 2),
+    (0.0, 512.0, 256), (-1.0, 80.0, 10),
+])
+def test_fast_divide_is_ieee_divide_exhaustively(engine, lo, hi, nbins):
+    """All 2^32 fp32 bit patterns: the branch-free divide of the fast kernels bins exactly like __fdiv_rn."""
+    used, bad = engine.selftest_fastdiv(lo, hi, nbins)
+    if used:
+        assert bad == 0
+
+
+def test_unsafe_divisors_take_the_ieee_kernel(engine):
+    # w with an all-ones significand (Markstein's exception) and w outside the safe exponent window
+    w_bad = np.float32(np.uint32(0x3FFFFFFF).view(np.float32))          # 1.9999999
+    for lo, hi, nbins in [(0.0, float(w_bad * np.float32(4)), 4), (0.0, 1e-37, 8), (-1e38, 1e38, 2)]:
+        used, _ = engine.selftest_fastdiv(lo, hi, nbins)
+        assert not used
+        rng = np.random.default_rng(3)
+        x = rng.uniform(lo, hi, 200_000)
+        x[::7] = hi; x[::11] = lo
+        t = engine.table_from_numpy(x[None, :])
+        got = engine.project_cast_hist(t, [0], nbins, lo, hi).to_numpy()
+        _, exp = bn.project_cast_hist(x[None, :], [0], nbins, [lo], [hi])
+        np.testing.assert_array_equal(got, exp)
+        t.free()
