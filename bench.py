@@ -113,6 +113,7 @@ def cpu_pass_setup(sample_rows: int, ncols: int):
     from learningorchestra_b200.build import build_oracle
     build_oracle()
     from oracle import cport
+    cport.use_all_cores()
     cols = [cport.synth_f64(0, SEED, c, 0, sample_rows, GEN_LO, GEN_HI) for c in range(ncols)]
     proj = [cols[c] for c in projected_columns(ncols)]
     lo = np.full(ncols, GEN_LO, np.float32)
@@ -201,8 +202,8 @@ def run_gpu(args) -> None:
 
     eng = Engine(local_rank)
     ncols, total_rows = args.cols, args.rows
-    r_begin = (total_rows * rank) // world
-    r_end = (total_rows * (rank + 1)) // world
+    from learningorchestra_b200.sharding import allreduce_counts, shard_bounds
+    r_begin, r_end = shard_bounds(total_rows, world, rank)
     nrows = r_end - r_begin
     cols = projected_columns(ncols)
     k = len(cols)
@@ -231,7 +232,7 @@ def run_gpu(args) -> None:
             e1.record(stream)
             kev.append((e0, e1))
         if world > 1:
-            dist.all_reduce(counts_t, op=dist.ReduceOp.SUM)
+            allreduce_counts(counts_t)          # ONE ncclAllReduce of k*nbins int64 over NVLink, same stream
 
     for _ in range(args.warmup):
         step(False)
@@ -334,7 +335,9 @@ def run_gpu(args) -> None:
         tr = ROOT / "profiles" / "traffic.json"
         if tr.exists():
             try:
-                line["roofline"]["traffic"] = json.loads(tr.read_text()).get("k_project_cast_hist_bytes_per_launch")
+                t100 = json.loads(tr.read_text()).get("k_project_cast_hist_bytes_per_launch")   # ncu, 100M-row launch
+                line["roofline"]["traffic"] = t100 * nrows / 100_000_000 if t100 else None
+                line["roofline"]["traffic_source"] = "ncu --set full dram__bytes_read+write of one 100M x 32 launch (profiles/), scaled to this launch's rows"
             except Exception:
                 pass
         print(json.dumps(line), flush=True)

@@ -259,6 +259,15 @@ void oracle_synth_hist_u8(uint64_t seed, int64_t row0, int64_t nrows, const int3
     }
 }
 
+/* torchrun exports OMP_NUM_THREADS=1; the CPU arm wants every core the process may run on */
+void oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int oracle_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -38,6 +38,14 @@ def num_threads() -> int:
     return int(lib().oracle_num_threads())
 
 
+def use_all_cores() -> int:
+    """Let OpenMP use every core this process may run on (torchrun exports OMP_NUM_THREADS=1)."""
+    import os
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().oracle_set_num_threads(C.c_int(n))
+    return num_threads()
+
+
 def cast_f64_f32(x: np.ndarray) -> np.ndarray:
     x = np.ascontiguousarray(x, dtype=np.float64)
     out = np.empty(x.shape, dtype=np.float32)
