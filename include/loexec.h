@@ -54,6 +54,7 @@ extern "C" {
 #define LO_F64 1   /* IEEE binary64 */
 #define LO_F32 2   /* IEEE binary32 */
 #define LO_U8  3   /* unsigned byte */
+#define LO_U32 4   /* dictionary codes (host entry points only) */
 
 /* synthetic generators (oracle/synth.py and oracle/bsem.c hold the CPU twins) */
 #define LO_SYNTH_UNIFORM   0  /* f64: lo + (hi-lo) * (splitmix64(...)>>11) * 2^-53            */
@@ -168,6 +169,18 @@ int lo_project_cast_hist_host(lo_ctx *ctx, const double *const *in_cols, int64_t
 /* in_cols[j]: host pointer to nrows bytes; counts: host uint64[k*256], overwritten */
 int lo_hist_u8_cols_host(lo_ctx *ctx, const uint8_t *const *in_cols, int64_t nrows, int32_t k,
                          uint64_t *counts, lo_host_timing *timing);
+
+/* Exact value counts of one dictionary-encoded column (R-semantics `$group`/`$sum:1`,
+ * histogram_image/histogram.py:31-36, for columns with more than 256 distinct keys):
+ * counts[c] = number of rows whose code is c; counts: host uint64[ncodes], overwritten.
+ * A code >= ncodes fails with LO_ERR_INVALID. */
+int lo_value_counts_u32_host(lo_ctx *ctx, const uint32_t *codes, int64_t nrows, uint32_t ncodes,
+                             uint64_t *counts, lo_host_timing *timing);
+/* Per-column min and max of the CAST fp32 values over finite entries (NaN / +-inf ignored): the
+ * range pre-pass for a histogram request that carries no range.
+ * mins / maxs: host float[k]; nfinite: host uint64[k] (0 -> min = max = 0). */
+int lo_minmax_cast_host(lo_ctx *ctx, const double *const *in_cols, int64_t nrows, int32_t k,
+                        float *mins, float *maxs, uint64_t *nfinite, lo_host_timing *timing);
 
 #ifdef __cplusplus
 }

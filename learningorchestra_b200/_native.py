@@ -23,7 +23,7 @@ LO_ERR_NOT_IMPLEMENTED = -4
 LO_ERR_NO_DEVICE = -5
 LO_ERR_ALIGNMENT = -6
 
-LO_F64, LO_F32, LO_U8 = 1, 2, 3
+LO_F64, LO_F32, LO_U8, LO_U32 = 1, 2, 3, 4
 LO_SYNTH_UNIFORM, LO_SYNTH_EDGES, LO_SYNTH_CONSTCOL, LO_SYNTH_MNIST_U8 = 0, 1, 2, 3
 LO_MAX_BINS = 256
 LO_ABI_VERSION = 1
@@ -87,6 +87,8 @@ SIGNATURES = {
     "lo_project_cast_hist_host": (C.c_int, [_P, C.POINTER(_P), C.c_int64, C.c_int32, C.POINTER(_P),
                                             C.POINTER(HistSpec), _P, C.POINTER(HostTiming)]),
     "lo_hist_u8_cols_host": (C.c_int, [_P, C.POINTER(_P), C.c_int64, C.c_int32, _P, C.POINTER(HostTiming)]),
+    "lo_value_counts_u32_host": (C.c_int, [_P, _P, C.c_int64, C.c_uint32, _P, C.POINTER(HostTiming)]),
+    "lo_minmax_cast_host": (C.c_int, [_P, C.POINTER(_P), C.c_int64, C.c_int32, _P, _P, _P, C.POINTER(HostTiming)]),
 }
 
 _lib = None

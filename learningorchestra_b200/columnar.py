@@ -1,0 +1,81 @@
+"""Documents <-> columns: the adapter either side of the GPU path.
+
+The reference's table is one Mongo document per row (``database_api_image/database.py:124-137``);
+the kernels want one contiguous slab per column.  This module does only that reshaping (plus the
+dictionary encoding that turns arbitrary keys into dense codes) — never the arithmetic.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+METADATA_DOCUMENT_ID = 0
+_EXACT_INT = 2 ** 53
+
+
+def data_rows(documents):
+    """``dataframe.filter(dataframe["_id"] != 0)`` (``projection.py:38-40``)."""
+    return [d for d in documents if d.get("_id") != METADATA_DOCUMENT_ID]
+
+
+def numeric_column(values):
+    """(float64 array with NaN at nulls, valid mask, kind) or None if the column is not numeric.
+    kind "int": every non-null value is an int that float64 holds exactly; "float": ints and floats mixed
+    (what the Mongo-Spark connector's schema inference widens to double)."""
+    n = len(values)
+    out = np.empty(n, dtype=np.float64)
+    valid = np.ones(n, dtype=bool)
+    all_int = True
+    for i, v in enumerate(values):
+        if v is None:
+            out[i] = math.nan
+            valid[i] = False
+        elif isinstance(v, bool):
+            return None
+        elif isinstance(v, int):
+            if abs(v) > _EXACT_INT:
+                return None
+            out[i] = float(v)
+        elif isinstance(v, float):
+            all_int = False
+            out[i] = v
+        else:
+            return None
+    return out, valid, ("int" if all_int else "float")
+
+
+def group_key(value):
+    """Canonical key under MongoDB ``$group`` equality: numbers by value across int / float (1 == 1.0,
+    -0.0 == 0.0), NaN with NaN, null and missing together, booleans apart from numbers, strings bytewise."""
+    if value is None:
+        return ("null",)
+    if isinstance(value, bool):
+        return ("bool", value)
+    if isinstance(value, (int, float)):
+        if isinstance(value, float):
+            if math.isnan(value):
+                return ("num", "nan")
+            if math.isinf(value):
+                return ("num", "inf" if value > 0 else "-inf")
+            if value.is_integer():
+                return ("num", int(value))
+        return ("num", value)
+    if isinstance(value, str):
+        return ("str", value)
+    return ("other", repr(value))
+
+
+def dictionary_encode(values):
+    """Dense codes in first-seen order: (codes uint32, representatives list)."""
+    index: dict = {}
+    reps = []
+    codes = np.empty(len(values), dtype=np.uint32)
+    for i, v in enumerate(values):
+        k = group_key(v)
+        c = index.get(k)
+        if c is None:
+            c = index[k] = len(reps)
+            reps.append(v)
+        codes[i] = c
+    return codes, reps

@@ -481,6 +481,51 @@ __global__ void k_fill_u8_mnist(uint8_t *base, long long pitch, long long nrows,
     }
 }
 
+// exact value counts of dictionary codes (R-semantics $group on arbitrary columns): RED.64 per element;
+// counts[ncodes] collects out-of-range codes so the host can reject them
+__global__ void k_count_codes_u32(const uint32_t *__restrict__ codes, long long n, uint32_t ncodes,
+                                  unsigned long long *__restrict__ counts) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const uint32_t c = codes[i];
+        atomicAdd(counts + (c < ncodes ? c : ncodes), 1ull);
+    }
+}
+
+// per-column min / max / count of the finite cast values.  out[3*j+0] = max over ~ordered(x) (i.e. the
+// min, stored complemented so that zero-filled memory is the identity), out[3*j+1] = max over ordered(x),
+// out[3*j+2] = count;  ordered(bits) maps fp32 to uint32 monotonically.
+__device__ __forceinline__ uint32_t ordered_u32(float f) {
+    const uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+__global__ void k_minmax_cast(const char *__restrict__ base, long long pitch, long long n,
+                              unsigned long long *__restrict__ out) {
+    const double *col = reinterpret_cast<const double *>(base + (long long)blockIdx.y * pitch);
+    uint32_t mn = 0, mx = 0;
+    unsigned long long cnt = 0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float f = cast_f64_f32(col[i]);
+        if (f == f && fabsf(f) != __int_as_float(0x7f800000)) {
+            const uint32_t o = ordered_u32(f);
+            mn = max(mn, ~o);
+            mx = max(mx, o);
+            ++cnt;
+        }
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        mn = max(mn, __shfl_xor_sync(0xffffffffu, mn, s));
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, s));
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, s);
+    }
+    if ((threadIdx.x & 31) == 0 && cnt) {
+        atomicMax(out + 3 * blockIdx.y + 0, (unsigned long long)mn);
+        atomicMax(out + 3 * blockIdx.y + 1, (unsigned long long)mx);
+        atomicAdd(out + 3 * blockIdx.y + 2, cnt);
+    }
+}
+
 // exhaustive self-test: every one of the 2^32 fp32 bit patterns through both divide variants
 __global__ void k_selftest_fastdiv(float lo, float hi, float w, int nbins, unsigned long long *mismatches) {
     BinParams B = {lo, hi, w, __frcp_rn(w), nbins - 1};

@@ -53,6 +53,7 @@ size_t dtype_size(int dtype) {
         case LO_F64: return 8;
         case LO_F32: return 4;
         case LO_U8:  return 1;
+        case LO_U32: return 4;
         default:     return 0;
     }
 }
@@ -644,62 +645,56 @@ int lo_counts_download(lo_ctx *ctx, const uint64_t *counts_dev, int64_t n, uint6
 //   h2d stream : wait(kernel of chunk c-2 done)  -> k column copies          -> ev_h2d[slot]
 //   compute    : wait(ev_h2d[slot]), wait(d2h of chunk c-2 done) -> kernel   -> ev_k[slot]
 //   d2h stream : wait(ev_k[slot]) -> k column copies back                    -> ev_d2h[slot]
-int lo_project_cast_hist_host(lo_ctx *ctx, const double *const *in_cols, int64_t nrows, int32_t k,
-                              float *const *out_cols, const lo_hist_spec *spec, uint64_t *counts,
-                              lo_host_timing *timing) {
-    LO_TRY(check_ctx(ctx));
-    if (k <= 0) return fail(LO_ERR_INVALID, "k must be > 0 (got %d)", k);
-    if (nrows < 0) return fail(LO_ERR_INVALID, "nrows < 0");
-    if (!in_cols) return fail(LO_ERR_INVALID, "in_cols is NULL");
-    if (!out_cols && !spec) return fail(LO_ERR_INVALID, "nothing to do: no out_cols and no spec");
-    if (spec && !counts) return fail(LO_ERR_INVALID, "counts is NULL");
-    for (int j = 0; j < k; ++j) {
-        if (nrows > 0 && !in_cols[j]) return fail(LO_ERR_INVALID, "in_cols[%d] is NULL", j);
-        if (nrows > 0 && out_cols && !out_cols[j]) return fail(LO_ERR_INVALID, "out_cols[%d] is NULL", j);
-    }
-    std::vector<float> w(k);
-    if (spec) LO_TRY(check_spec(spec, k, w.data()));
+// `launch(tin, tout_or_null)` enqueues the kernel(s) of one chunk on ctx->stream.
+}  // extern "C"
+
+namespace {
+
+template <typename Launch>
+int host_pipeline(lo_ctx *ctx, const void *const *in_cols, int in_dtype, int64_t nrows, int32_t k,
+                  void *const *out_cols, int out_dtype, int64_t tile_rows, size_t ncounts, uint64_t *counts_host,
+                  lo_host_timing *timing, Launch launch) {
     const auto t0 = std::chrono::steady_clock::now();
     const int64_t launches0 = ctx->launches.load();
-    const size_t ncounts = spec ? (size_t)k * (size_t)spec->nbins : 0;
-    if (spec) memset(counts, 0, ncounts * 8);
+    const size_t ies = dtype_size(in_dtype), oes = out_cols ? dtype_size(out_dtype) : 0;
     double h2d = 0, d2h = 0;
+    if (counts_host && ncounts) memset(counts_host, 0, ncounts * 8);
     if (nrows > 0) {
         std::lock_guard<std::mutex> lk(ctx->host_mu);
-        const int64_t crows = chunk_rows_for(nrows, k, 8, lo::kTileRows);
-        const int64_t in_pitch = crows * 8, out_pitch = crows * 4;   // multiples of 256
+        const int64_t crows = chunk_rows_for(nrows, k, ies, tile_rows);
+        const int64_t in_pitch  = (int64_t)(((size_t)crows * ies + 255) / 256 * 256);
+        const int64_t out_pitch = (int64_t)(((size_t)crows * oes + 255) / 256 * 256);
         LO_TRY(ensure_stage(ctx, (size_t)in_pitch * k, out_cols ? (size_t)out_pitch * k : 0, ncounts));
-        if (spec) LO_CUDA(cudaMemsetAsync(ctx->host_counts_dev, 0, ncounts * 8, ctx->stream));
-        std::vector<int32_t> ident(k);
-        for (int j = 0; j < k; ++j) ident[j] = j;
+        if (ncounts) LO_CUDA(cudaMemsetAsync(ctx->host_counts_dev, 0, ncounts * 8, ctx->stream));
         const int64_t nchunks = (nrows + crows - 1) / crows;
         for (int64_t c = 0; c < nchunks; ++c) {
             const int slot = (int)(c & 1);
             const int64_t r0 = c * crows, n = std::min(crows, nrows - r0);
             if (c >= 2) LO_CUDA(cudaStreamWaitEvent(ctx->h2d, ctx->ev_k[slot], 0));
             for (int j = 0; j < k; ++j)
-                LO_CUDA(cudaMemcpyAsync(ctx->stage_in[slot] + (int64_t)j * in_pitch, in_cols[j] + r0, (size_t)n * 8,
+                LO_CUDA(cudaMemcpyAsync(ctx->stage_in[slot] + (int64_t)j * in_pitch,
+                                        (const char *)in_cols[j] + r0 * (int64_t)ies, (size_t)n * ies,
                                         cudaMemcpyHostToDevice, ctx->h2d));
-            h2d += (double)n * 8 * k;
+            h2d += (double)n * ies * k;
             LO_CUDA(cudaEventRecord(ctx->ev_h2d[slot], ctx->h2d));
             LO_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[slot], 0));
             if (c >= 2 && out_cols) LO_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[slot], 0));
-            lo_table tin  = {LO_F64, n, k, in_pitch, ctx->stage_in[slot], false, ctx->device};
-            lo_table tout = {LO_F32, n, k, out_pitch, out_cols ? ctx->stage_out[slot] : nullptr, false, ctx->device};
-            LO_TRY(project_cast_hist_impl(ctx, &tin, ident.data(), k, out_cols ? &tout : nullptr, spec,
-                                          (uint64_t *)ctx->host_counts_dev, ctx->stream));
+            lo_table tin  = {in_dtype, n, k, in_pitch, ctx->stage_in[slot], false, ctx->device};
+            lo_table tout = {out_dtype, n, k, out_pitch, out_cols ? ctx->stage_out[slot] : nullptr, false, ctx->device};
+            LO_TRY(launch(&tin, out_cols ? &tout : nullptr));
             LO_CUDA(cudaEventRecord(ctx->ev_k[slot], ctx->stream));
             if (out_cols) {
                 LO_CUDA(cudaStreamWaitEvent(ctx->d2h, ctx->ev_k[slot], 0));
                 for (int j = 0; j < k; ++j)
-                    LO_CUDA(cudaMemcpyAsync(out_cols[j] + r0, ctx->stage_out[slot] + (int64_t)j * out_pitch,
-                                            (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->d2h));
-                d2h += (double)n * 4 * k;
+                    LO_CUDA(cudaMemcpyAsync((char *)out_cols[j] + r0 * (int64_t)oes,
+                                            ctx->stage_out[slot] + (int64_t)j * out_pitch, (size_t)n * oes,
+                                            cudaMemcpyDeviceToHost, ctx->d2h));
+                d2h += (double)n * oes * k;
                 LO_CUDA(cudaEventRecord(ctx->ev_d2h[slot], ctx->d2h));
             }
         }
-        if (spec) {
-            LO_CUDA(cudaMemcpyAsync(counts, ctx->host_counts_dev, ncounts * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        if (ncounts && counts_host) {
+            LO_CUDA(cudaMemcpyAsync(counts_host, ctx->host_counts_dev, ncounts * 8, cudaMemcpyDeviceToHost, ctx->stream));
             d2h += (double)ncounts * 8;
         }
         LO_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -715,52 +710,102 @@ int lo_project_cast_hist_host(lo_ctx *ctx, const double *const *in_cols, int64_t
     return LO_OK;
 }
 
+int check_host_cols(const void *const *cols, int64_t nrows, int32_t k, const char *what) {
+    if (k <= 0) return fail(LO_ERR_INVALID, "k must be > 0 (got %d)", k);
+    if (nrows < 0) return fail(LO_ERR_INVALID, "nrows < 0");
+    if (!cols) return fail(LO_ERR_INVALID, "%s is NULL", what);
+    for (int j = 0; j < k; ++j)
+        if (nrows > 0 && !cols[j]) return fail(LO_ERR_INVALID, "%s[%d] is NULL", what, j);
+    return LO_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lo_project_cast_hist_host(lo_ctx *ctx, const double *const *in_cols, int64_t nrows, int32_t k,
+                              float *const *out_cols, const lo_hist_spec *spec, uint64_t *counts,
+                              lo_host_timing *timing) {
+    LO_TRY(check_ctx(ctx));
+    LO_TRY(check_host_cols((const void *const *)in_cols, nrows, k, "in_cols"));
+    if (out_cols) LO_TRY(check_host_cols((const void *const *)out_cols, nrows, k, "out_cols"));
+    if (!out_cols && !spec) return fail(LO_ERR_INVALID, "nothing to do: no out_cols and no spec");
+    if (spec && !counts) return fail(LO_ERR_INVALID, "counts is NULL");
+    std::vector<float> w(k);
+    if (spec) LO_TRY(check_spec(spec, k, w.data()));
+    std::vector<int32_t> ident(k);
+    for (int j = 0; j < k; ++j) ident[j] = j;
+    const size_t ncounts = spec ? (size_t)k * (size_t)spec->nbins : 0;
+    return host_pipeline(ctx, (const void *const *)in_cols, LO_F64, nrows, k, (void *const *)out_cols, LO_F32,
+                         lo::kTileRows, ncounts, counts, timing, [&](lo_table *tin, lo_table *tout) {
+                             return project_cast_hist_impl(ctx, tin, ident.data(), k, tout, spec,
+                                                           (uint64_t *)ctx->host_counts_dev, ctx->stream);
+                         });
+}
+
 int lo_hist_u8_cols_host(lo_ctx *ctx, const uint8_t *const *in_cols, int64_t nrows, int32_t k, uint64_t *counts,
                          lo_host_timing *timing) {
     LO_TRY(check_ctx(ctx));
-    if (k <= 0) return fail(LO_ERR_INVALID, "k must be > 0 (got %d)", k);
-    if (nrows < 0) return fail(LO_ERR_INVALID, "nrows < 0");
-    if (!in_cols || !counts) return fail(LO_ERR_INVALID, "NULL argument");
-    for (int j = 0; j < k; ++j)
-        if (nrows > 0 && !in_cols[j]) return fail(LO_ERR_INVALID, "in_cols[%d] is NULL", j);
-    const auto t0 = std::chrono::steady_clock::now();
-    const int64_t launches0 = ctx->launches.load();
-    const size_t ncounts = (size_t)k * 256;
-    memset(counts, 0, ncounts * 8);
-    double h2d = 0, d2h = 0;
-    if (nrows > 0) {
-        std::lock_guard<std::mutex> lk(ctx->host_mu);
-        const int64_t crows = chunk_rows_for(nrows, k, 1, lo::kU8TileRows);
-        const int64_t pitch = crows;   // multiple of 61440 -> multiple of 256
-        LO_TRY(ensure_stage(ctx, (size_t)pitch * k, 0, ncounts));
-        LO_CUDA(cudaMemsetAsync(ctx->host_counts_dev, 0, ncounts * 8, ctx->stream));
-        std::vector<int32_t> ident(k);
-        for (int j = 0; j < k; ++j) ident[j] = j;
-        const int64_t nchunks = (nrows + crows - 1) / crows;
-        for (int64_t c = 0; c < nchunks; ++c) {
-            const int slot = (int)(c & 1);
-            const int64_t r0 = c * crows, n = std::min(crows, nrows - r0);
-            if (c >= 2) LO_CUDA(cudaStreamWaitEvent(ctx->h2d, ctx->ev_k[slot], 0));
-            for (int j = 0; j < k; ++j)
-                LO_CUDA(cudaMemcpyAsync(ctx->stage_in[slot] + (int64_t)j * pitch, in_cols[j] + r0, (size_t)n,
-                                        cudaMemcpyHostToDevice, ctx->h2d));
-            h2d += (double)n * k;
-            LO_CUDA(cudaEventRecord(ctx->ev_h2d[slot], ctx->h2d));
-            LO_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[slot], 0));
-            lo_table tin = {LO_U8, n, k, pitch, ctx->stage_in[slot], false, ctx->device};
-            LO_TRY(hist_u8_impl(ctx, &tin, ident.data(), k, (uint64_t *)ctx->host_counts_dev, ctx->stream));
-            LO_CUDA(cudaEventRecord(ctx->ev_k[slot], ctx->stream));
-        }
-        LO_CUDA(cudaMemcpyAsync(counts, ctx->host_counts_dev, ncounts * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        d2h += (double)ncounts * 8;
-        LO_CUDA(cudaStreamSynchronize(ctx->stream));
-        LO_CUDA(cudaStreamSynchronize(ctx->h2d));
-    }
-    if (timing) {
-        timing->total_ms  = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-        timing->h2d_bytes = h2d;
-        timing->d2h_bytes = d2h;
-        timing->launches  = ctx->launches.load() - launches0;
+    LO_TRY(check_host_cols((const void *const *)in_cols, nrows, k, "in_cols"));
+    if (!counts) return fail(LO_ERR_INVALID, "counts is NULL");
+    std::vector<int32_t> ident(k);
+    for (int j = 0; j < k; ++j) ident[j] = j;
+    return host_pipeline(ctx, (const void *const *)in_cols, LO_U8, nrows, k, nullptr, LO_U8, lo::kU8TileRows,
+                         (size_t)k * 256, counts, timing, [&](lo_table *tin, lo_table *) {
+                             return hist_u8_impl(ctx, tin, ident.data(), k, (uint64_t *)ctx->host_counts_dev, ctx->stream);
+                         });
+}
+
+// exact value counts of dictionary-encoded columns: counts[c] = #{r : codes[r] == c}
+int lo_value_counts_u32_host(lo_ctx *ctx, const uint32_t *codes, int64_t nrows, uint32_t ncodes, uint64_t *counts,
+                             lo_host_timing *timing) {
+    LO_TRY(check_ctx(ctx));
+    if (nrows < 0 || ncodes == 0) return fail(LO_ERR_INVALID, "bad arguments (nrows %lld, ncodes %u)", (long long)nrows, ncodes);
+    if ((nrows > 0 && !codes) || !counts) return fail(LO_ERR_INVALID, "NULL argument");
+    const void *cols[1] = {codes};
+    // counts buffer layout: [ncodes counts][1 out-of-range flag]
+    std::vector<uint64_t> tmp((size_t)ncodes + 1);
+    int rc = host_pipeline(ctx, cols, LO_U32, nrows, 1, nullptr, LO_U32, 1 << 16, (size_t)ncodes + 1, tmp.data(), timing,
+                           [&](lo_table *tin, lo_table *) {
+                               const int grid = ctx->sm_count * 8;
+                               lo::k_count_codes_u32<<<grid, 256, 0, ctx->stream>>>(
+                                   (const uint32_t *)tin->base, tin->nrows, ncodes, ctx->host_counts_dev);
+                               LO_CUDA(cudaGetLastError());
+                               ctx->launches.fetch_add(1, std::memory_order_relaxed);
+                               return LO_OK;
+                           });
+    LO_TRY(rc);
+    if (tmp[ncodes] != 0) return fail(LO_ERR_INVALID, "%llu codes were >= ncodes (%u)", (unsigned long long)tmp[ncodes], ncodes);
+    memcpy(counts, tmp.data(), (size_t)ncodes * 8);
+    return LO_OK;
+}
+
+// per-column min / max of the CAST fp32 values, ignoring NaN and +-inf (the range pre-pass when a
+// histogram request carries no range); nfinite[j] = how many values took part
+int lo_minmax_cast_host(lo_ctx *ctx, const double *const *in_cols, int64_t nrows, int32_t k, float *mins, float *maxs,
+                        uint64_t *nfinite, lo_host_timing *timing) {
+    LO_TRY(check_ctx(ctx));
+    LO_TRY(check_host_cols((const void *const *)in_cols, nrows, k, "in_cols"));
+    if (!mins || !maxs || !nfinite) return fail(LO_ERR_INVALID, "NULL argument");
+    // counts buffer layout per column: [ordered-uint min][ordered-uint max][count]
+    std::vector<uint64_t> tmp((size_t)k * 3);
+    int rc = host_pipeline(ctx, (const void *const *)in_cols, LO_F64, nrows, k, nullptr, LO_F32, lo::kTileRows,
+                           (size_t)k * 3, tmp.data(), timing, [&](lo_table *tin, lo_table *) {
+                               dim3 grid((unsigned)std::min<int64_t>((tin->nrows + 2047) / 2048, ctx->sm_count * 4), (unsigned)k);
+                               lo::k_minmax_cast<<<grid, 256, 0, ctx->stream>>>(
+                                   (const char *)tin->base, tin->pitch, tin->nrows, ctx->host_counts_dev);
+                               LO_CUDA(cudaGetLastError());
+                               ctx->launches.fetch_add(1, std::memory_order_relaxed);
+                               return LO_OK;
+                           });
+    LO_TRY(rc);
+    for (int j = 0; j < k; ++j) {
+        nfinite[j] = tmp[(size_t)j * 3 + 2];
+        // the device kept min as ~ordered (so that zero-initialised memory is the identity) and max as ordered
+        uint32_t omin = ~(uint32_t)tmp[(size_t)j * 3 + 0], omax = (uint32_t)tmp[(size_t)j * 3 + 1];
+        auto unorder = [](uint32_t o) { uint32_t b = (o & 0x80000000u) ? (o ^ 0x80000000u) : ~o; float f; memcpy(&f, &b, 4); return f; };
+        mins[j] = nfinite[j] ? unorder(omin) : 0.f;
+        maxs[j] = nfinite[j] ? unorder(omax) : 0.f;
     }
     return LO_OK;
 }

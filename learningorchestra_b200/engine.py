@@ -264,3 +264,22 @@ class Engine:
         N.check(self._lib.lo_hist_u8_cols_host(self._ctx, in_p, n, k, counts.ctypes.data_as(C.c_void_p), C.byref(timing)))
         return counts, {"total_ms": timing.total_ms, "h2d_bytes": timing.h2d_bytes, "d2h_bytes": timing.d2h_bytes,
                         "launches": timing.launches}
+
+    def value_counts_u32_host(self, codes: np.ndarray, ncodes: int) -> np.ndarray:
+        """counts[c] = number of entries of ``codes`` (uint32, dictionary encoded) equal to c."""
+        codes = np.ascontiguousarray(codes, dtype=np.uint32)
+        counts = np.zeros(int(ncodes), dtype=np.uint64)
+        N.check(self._lib.lo_value_counts_u32_host(self._ctx, codes.ctypes.data_as(C.c_void_p), codes.shape[0],
+                                                   int(ncodes), counts.ctypes.data_as(C.c_void_p), None))
+        return counts
+
+    def minmax_cast_host(self, cols: Sequence[np.ndarray]):
+        """(min, max, n_finite) per column of the fp32-cast values, NaN / inf ignored."""
+        k = len(cols)
+        cols = [np.ascontiguousarray(c, dtype=np.float64) for c in cols]
+        n = cols[0].shape[0] if k else 0
+        in_p = (C.c_void_p * k)(*[c.ctypes.data for c in cols])
+        mins, maxs, cnt = np.zeros(k, np.float32), np.zeros(k, np.float32), np.zeros(k, np.uint64)
+        N.check(self._lib.lo_minmax_cast_host(self._ctx, in_p, n, k, mins.ctypes.data_as(C.c_void_p),
+                                              maxs.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.c_void_p), None))
+        return mins, maxs, cnt

@@ -1,0 +1,100 @@
+"""``Histogram`` — drop-in for ``histogram_image/histogram.py`` (same constructor and ``create_file``).
+
+Reference job (``histogram.py:25-44``): per requested field one MongoDB pipeline
+``[{"$group": {"_id": "$field", "count": {"$sum": 1}}}]`` over the WHOLE parent collection (metadata
+document included: it has no such field, so it lands in — and inflates — the ``null`` group), one result
+document ``{field: [{"_id": value, "count": n}, ...], "_id": k}`` per field, then ``finished: True``.
+
+Here the counting runs on the GPU.  The adapter dictionary-encodes each field's values (MongoDB's
+grouping equality, :func:`columnar.group_key`) into dense codes; fields with <= 256 distinct keys are
+packed into byte columns and counted together by ``k_hist_u8_cols`` (per-thread byte-counter
+histograms, ``lo_hist_u8_cols_host``), larger dictionaries by ``k_count_codes_u32``
+(``lo_value_counts_u32_host``).  With ``bins`` (optional extension, REST key ``bins`` / ``range``) the
+fields must be numeric and get the fixed-width B-semantics histogram of SURVEY.md §8c from the fused
+kernel instead.
+"""
+from __future__ import annotations
+
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+from . import columnar
+from .utils import record_exception
+
+
+class Histogram:
+    METADATA_DOCUMENT_ID = 0
+    DOCUMENT_ID_NAME = "_id"
+
+    def __init__(self, database_connector, metadata_handler, engine=None):
+        self.database_connector = database_connector
+        self.metadata_handler = metadata_handler
+        self.thread_pool = ThreadPoolExecutor()
+        self.engine = engine
+        self.last_job = None
+
+    def create_file(self, parent_filename, histogram_filename, fields, bins=None, value_range=None):
+        self.metadata_handler.create_file(parent_filename, histogram_filename, fields)
+        self.last_job = self.thread_pool.submit(self.file_processing, parent_filename, histogram_filename, fields,
+                                                bins, value_range)
+
+    def wait(self, timeout=None):
+        if self.last_job is not None:
+            self.last_job.result(timeout)
+
+    def file_processing(self, parent_filename, histogram_filename, fields, bins=None, value_range=None):
+        try:
+            if self.engine is None:
+                raise RuntimeError("Histogram needs an Engine: the counting has no CPU fallback")
+            documents = self.database_connector.find(parent_filename, {})      # unfiltered, like $group
+            if bins:
+                results = self.__binned(documents, fields, int(bins), value_range)
+            else:
+                results = self.__value_counts(documents, fields)
+            document_id = 1
+            for field in fields:
+                self.database_connector.insert_one_in_file(
+                    histogram_filename, {field: results[field], self.DOCUMENT_ID_NAME: document_id})
+                document_id += 1
+            self.metadata_handler.update_finish_flag(histogram_filename, True)
+        except BaseException as exc:
+            record_exception(self.database_connector, histogram_filename, exc)
+            raise
+
+    # ---- R-semantics: exact value counts -------------------------------------------------------------
+    def __value_counts(self, documents, fields):
+        encoded = {f: columnar.dictionary_encode([d.get(f) for d in documents]) for f in fields}
+        results = {}
+        small = [f for f in fields if len(encoded[f][1]) <= 256]
+        if small and documents:
+            cols = [encoded[f][0].astype(np.uint8) for f in small]
+            counts, _ = self.engine.hist_u8_cols_host(cols)
+            for j, f in enumerate(small):
+                reps = encoded[f][1]
+                results[f] = [{"_id": reps[c], "count": int(counts[j][c])} for c in range(len(reps))]
+        for f in fields:
+            if f in results:
+                continue
+            codes, reps = encoded[f]
+            counts = self.engine.value_counts_u32_host(codes, max(len(reps), 1)) if len(codes) else []
+            results[f] = [{"_id": reps[c], "count": int(counts[c])} for c in range(len(reps))]
+        return results
+
+    # ---- B-semantics: fixed-width bins of the fp32-cast value -----------------------------------------
+    def __binned(self, documents, fields, bins, value_range):
+        rows = columnar.data_rows(documents)
+        cols = []
+        for f in fields:
+            packed = columnar.numeric_column([d.get(f) for d in rows])
+            if packed is None:
+                raise ValueError(f"field {f!r} is not numeric; run /fieldTypes first")
+            cols.append(packed[0])          # nulls are NaN: skipped by the kernel
+        if value_range is None:
+            lo, hi, _cnt = self.engine.minmax_cast_host(cols)
+        else:
+            lo = np.full(len(fields), value_range[0], np.float32)
+            hi = np.full(len(fields), value_range[1], np.float32)
+        counts, _ = self.engine.project_cast_hist_host(cols, bins, lo, hi)
+        return {f: {"bins": bins, "range": [float(lo[j]), float(hi[j])], "counts": [int(c) for c in counts[j]]}
+                for j, f in enumerate(fields)}

@@ -1,0 +1,152 @@
+"""GPU: the reference-shaped executors (Projection / DataType / Histogram) and REST routes, with the
+counting / casting on the device, against (a) golden fixtures produced by the reference's own
+histogram.py / data_type_update.py and (b) the oracle."""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+from werkzeug.test import Client
+
+from learningorchestra_b200 import server, utils
+from learningorchestra_b200.data_type_update import DataType
+from learningorchestra_b200.histogram import Histogram
+from learningorchestra_b200.projection import Projection
+from oracle import bsem_numpy as bn
+from oracle import rsem
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).resolve().parent / "golden"
+
+
+def _load(name):
+    return json.loads((GOLD / name).read_text())
+
+
+def _titanic_db():
+    db = utils.Database()
+    g = _load("titanic_shaped_input.json")
+    headers, docs = rsem.csv_rows_to_documents(g["headers"], g["rows"])
+    db.insert_one_in_file("titanic", rsem.dataset_metadata("titanic", headers))
+    db.insert_many_in_file("titanic", docs)
+    return db
+
+
+def _url(name):
+    return utils.Database.collection_database_url("mongodb://x", "database", name, "rs")
+
+
+def test_titanic_histogram_value_counts_match_reference_execution(engine):
+    """Config T, R-semantics: string -> number cast, then per-field value counts ($group) on the GPU."""
+    db = _titanic_db()
+    job = DataType(db, utils.DataTypeMetadata(db), engine)
+    job.convert_existent_file("titanic", {"Survived": "number", "Pclass": "number", "Age": "number", "Fare": "number"})
+    job.wait()
+    gold = _load("reference_histogram.json")
+    h = Histogram(db, utils.HistogramMetadata(db), engine)
+    h.create_file("titanic", "titanic_hist", list(gold["fields"]))
+    h.wait()
+    got = sorted(db.find("titanic_hist", {}), key=lambda d: d["_id"])
+    ref = sorted(gold["documents"], key=lambda d: d["_id"])
+    assert got[0]["finished"] is True and got[0]["type"] == "explore/histogram" and got[0]["fields"] == gold["fields"]
+    assert [d["_id"] for d in got] == [d["_id"] for d in ref]
+    for mine, theirs, f in zip(got[1:], ref[1:], gold["fields"]):
+        assert set(mine) == {f, "_id"}
+        assert rsem.normalise_group_result(mine[f]) == rsem.normalise_group_result(theirs[f]), f
+
+
+def test_byte_table_value_counts_match_reference_execution(engine):
+    """Config M bridge: on byte columns the 256-bin histogram IS the reference's $group output."""
+    gold = _load("reference_histogram_bytes.json")
+    t = bn.synth_table_u8(gold["seed"], gold["ncols"], 0, gold["nrows"])
+    names = [f"px{c}" for c in gold["cols"]]
+    db = utils.Database()
+    db.insert_one_in_file("bytes", rsem.dataset_metadata("bytes", names))
+    db.insert_many_in_file("bytes", [dict({f"px{c}": int(t[c, r]) for c in gold["cols"]}, _id=r + 1)
+                                     for r in range(gold["nrows"])])
+    h = Histogram(db, utils.HistogramMetadata(db), engine)
+    h.create_file("bytes", "bytes_hist", list(names))
+    h.wait()
+    got = sorted((d for d in db.find("bytes_hist", {}) if d["_id"] != 0), key=lambda d: d["_id"])
+    ref = sorted((d for d in gold["documents"] if d["_id"] != 0), key=lambda d: d["_id"])
+    for mine, theirs, f in zip(got, ref, names):
+        assert rsem.normalise_group_result(mine[f]) == rsem.normalise_group_result(theirs[f])
+    # and directly through the device-resident kernel: counts[v] for v in 0..255 (+1 null for the metadata doc)
+    cols = [np.ascontiguousarray(t[c]) for c in gold["cols"]]
+    counts, _ = engine.hist_u8_cols_host(cols)
+    for j, (theirs, f) in enumerate(zip(ref, names)):
+        want = {g["_id"]: g["count"] for g in theirs[f] if g["_id"] is not None}
+        assert {v: int(n) for v, n in enumerate(counts[j]) if n} == want
+
+
+def test_high_cardinality_field_uses_code_counting_kernel(engine):
+    db = _titanic_db()          # PassengerId / Name / Ticket have > 256 distinct strings
+    h = Histogram(db, utils.HistogramMetadata(db), engine)
+    h.create_file("titanic", "hc", ["PassengerId", "Ticket", "Embarked"])
+    h.wait()
+    docs = db.find("titanic", {})
+    got = sorted((d for d in db.find("hc", {}) if d["_id"] != 0), key=lambda d: d["_id"])
+    for mine, f in zip(got, ["PassengerId", "Ticket", "Embarked"]):
+        assert rsem.normalise_group_result(mine[f]) == rsem.normalise_group_result(rsem.group_counts(docs, f))
+    rng = np.random.default_rng(1)
+    codes = rng.integers(0, 70_000, 1_000_003, dtype=np.uint32)
+    np.testing.assert_array_equal(engine.value_counts_u32_host(codes, 70_000), np.bincount(codes, minlength=70_000))
+    from learningorchestra_b200._native import LoexecError
+    with pytest.raises(LoexecError):
+        engine.value_counts_u32_host(codes, 69_000)
+
+
+def test_titanic_flow_project_cast_and_10_bin_histogram(engine):
+    """Config T, B-semantics extension: project 4 columns -> fp32 cast -> 10-bin histogram, fused on the GPU."""
+    db = _titanic_db()
+    c = Client(server.create_app(db, engine, synchronous=True))
+    fields = ["Survived", "Pclass", "Age", "Fare"]
+    assert c.patch("/fieldTypes", json={"inputDatasetName": "titanic", "types": {f: "number" for f in fields}}).status_code == 200
+    r = c.post("/projections", json={"inputDatasetName": "titanic", "outputDatasetName": "t4", "names": fields,
+                                     "castTo": "float32", "bins": 10})
+    assert r.status_code == 201
+    meta = db.find_one("t4", {"_id": 0})
+    assert meta["finished"] is True, meta
+    rows = sorted((d for d in db.find("titanic", {}) if d["_id"] != 0), key=lambda d: d["_id"])
+    out = {d["_id"]: d for d in db.find("t4", {}) if d["_id"] != 0}
+    for j, f in enumerate(fields):
+        vals = np.array([np.nan if d[f] is None else float(d[f]) for d in rows])
+        f32 = bn.cast_f64_f32(vals)
+        finite = f32[np.isfinite(f32)]
+        lo, hi = finite.min(), finite.max()
+        hist = meta["histogram"][f]
+        assert hist["bins"] == 10 and hist["range"] == [float(lo), float(hi)]
+        assert hist["counts"] == bn.hist_f32(f32, lo, hi, 10).tolist()
+        for d, x, raw in zip(rows, f32, vals):
+            got = out[d["_id"]][f]
+            assert (got is None and np.isnan(raw)) or np.float32(got) == x
+    # histogram endpoint with explicit range on the converted collection
+    r = c.post("/histograms", json={"inputDatasetName": "titanic", "outputDatasetName": "h10", "names": ["Age", "Fare"],
+                                    "bins": 10, "range": [0, 100]})
+    assert r.status_code == 201 and db.find_one("h10", {"_id": 0})["finished"] is True
+    for d, f in zip(sorted((d for d in db.find("h10", {}) if d["_id"] != 0), key=lambda d: d["_id"]), ["Age", "Fare"]):
+        vals = np.array([np.nan if r_[f] is None else float(r_[f]) for r_ in rows])
+        assert d[f]["counts"] == bn.hist_f32(bn.cast_f64_f32(vals), 0, 100, 10).tolist()
+
+
+def test_datatype_float32_extension(engine):
+    db = utils.Database()
+    vals = [0.1, 16777217, 1e39, None, -1e-46, 7.25, 3]
+    db.insert_one_in_file("v", rsem.dataset_metadata("v", ["x"]))
+    db.insert_many_in_file("v", [{"_id": i + 1, "x": v} for i, v in enumerate(vals)])
+    job = DataType(db, utils.DataTypeMetadata(db), engine)
+    job.convert_existent_file("v", {"x": "float32"})
+    job.wait()
+    got = [d["x"] for d in sorted(db.find("v", {}), key=lambda d: d["_id"]) if d["_id"] != 0]
+    exp = bn.cast_f64_f32(np.array([np.nan if v is None else float(v) for v in vals]))
+    for g, e, v in zip(got, exp, vals):
+        assert (v is None and g is None) or np.float32(g).view(np.uint32) == e.view(np.uint32)
+
+
+def test_minmax_prepass(engine):
+    table = bn.synth_table_f64(1, 20260921, 5, 0, 300_001)
+    mn, mx, cnt = engine.minmax_cast_host([table[c] for c in range(5)])
+    for c in range(5):
+        f = bn.cast_f64_f32(table[c])
+        fin = f[np.isfinite(f)]
+        assert mn[c] == fin.min() and mx[c] == fin.max() and cnt[c] == fin.size
