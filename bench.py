@@ -220,18 +220,31 @@ def run_gpu(args) -> None:
     hi = np.full(k, GEN_HI, np.float32)
     torch.cuda.synchronize()
 
+    peer = None
+    if world > 1 and args.merge == "p2p":
+        from learningorchestra_b200.sharding import PeerReduce
+        peer = PeerReduce(eng, k, NBINS)
+
     kev = []   # (start, end) events around the fused kernel only, for the roofline
 
     def step(record: bool):
-        counts.zero(stream)
+        if peer is not None:
+            # merge fused into the kernel's flush: system-scope REDs into the root's matrix over NVLink
+            peer.before_kernel(stream)
+            dst, is_peer = peer.counts_for_step(), True
+        else:
+            counts.zero(stream)
+            dst, is_peer = counts, False
         if record:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-        eng.project_cast_hist(table, cols, NBINS, lo, hi, out=out, counts=counts, stream=stream)
+        eng.project_cast_hist(table, cols, NBINS, lo, hi, out=out, counts=dst, stream=stream, peer_counts=is_peer)
         if record:
             e1.record(stream)
             kev.append((e0, e1))
-        if world > 1:
+        if peer is not None:
+            peer.after_kernel(stream)
+        elif world > 1:
             allreduce_counts(counts_t)          # ONE ncclAllReduce of k*nbins int64 over NVLink, same stream
 
     for _ in range(args.warmup):
@@ -261,9 +274,14 @@ def run_gpu(args) -> None:
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     elapsed_ms, kernel_ms_avg = float(t[0]), float(t[1])
-    final_counts = counts.to_numpy(stream)
-    total_counted = int(final_counts.sum())
-    assert total_counted == total_rows * k, f"histogram lost rows: {total_counted} != {total_rows * k}"
+    if peer is not None:
+        assert peer.timed_out(stream) == 0, "peer-memory merge timed out"
+        final_counts = peer.result_numpy(stream)
+    else:
+        final_counts = counts.to_numpy(stream)
+    if final_counts is not None:
+        total_counted = int(final_counts.sum())
+        assert total_counted == total_rows * k, f"histogram lost rows: {total_counted} != {total_rows * k}"
 
     # ---- end to end: host buffers in, host buffers out, through the plugin-facing C-ABI call ----------
     e2e = None
@@ -321,7 +339,9 @@ def run_gpu(args) -> None:
             "config": {"workload": f"fused project+cast+{NBINS}-bin histogram, {total_rows} x {ncols} fp64 -> fp32, "
                                    f"K={k} (permutation), columnar, range [{GEN_LO}, {GEN_HI}]",
                        "rows": total_rows, "cols": ncols, "k": k, "nbins": NBINS, "rows_per_gpu": nrows,
-                       "parallelism": f"row-range shards x{world}, one NCCL all-reduce of {k}x{NBINS} uint64 per step"
+                       "parallelism": (f"row-range shards x{world}, " + (
+                           f"one NCCL all-reduce of {k}x{NBINS} uint64 per step" if peer is None else
+                           "merge fused into the kernel flush: system-scope RED.64 into rank 0's matrix over NVLink (CUDA IPC)"))
                                       if world > 1 else "single GPU",
                        "l2": f"inputs larger than L2: {nrows * ncols * 8 / 1e9:.1f} GB read + "
                              f"{nrows * k * 4 / 1e9:.1f} GB written per GPU per step (L2 = 126 MB), no flush needed"},
@@ -360,6 +380,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--merge", default="nccl", choices=["nccl", "p2p"],
+                    help="N > 1: how partial histograms are merged (NCCL all-reduce, or fused peer-memory REDs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -62,6 +62,8 @@ extern "C" {
 #define LO_SYNTH_CONSTCOL  2  /* EDGES + column 0 constant (contention worst case)           */
 #define LO_SYNTH_MNIST_U8  3  /* u8: 28x28 image columns, border 0, ~80 % zeros overall      */
 
+#define LO_HIST_PEER_COUNTS 1 /* counts_dev may be PEER memory (lo_ipc_open): flush with system-scope REDs */
+
 #define LO_MAX_BINS 256       /* per-thread byte-counter histograms hold <= 256 bins          */
 
 typedef struct lo_ctx   lo_ctx;    /* one per (process, device) */
@@ -74,7 +76,7 @@ typedef struct lo_table lo_table;  /* columnar table: ncols slabs of nrows eleme
  *   lo/hi are HOST arrays of k floats.  Counts are uint64, layout [k][nbins]. */
 typedef struct lo_hist_spec {
     int32_t      nbins;     /* 1..LO_MAX_BINS */
-    int32_t      reserved;  /* must be 0 */
+    int32_t      flags;     /* 0, or LO_HIST_PEER_COUNTS */
     const float *lo;        /* k lower edges  */
     const float *hi;        /* k upper edges (closed) ; hi[j] > lo[j], both finite */
 } lo_hist_spec;
@@ -169,6 +171,30 @@ int lo_project_cast_hist_host(lo_ctx *ctx, const double *const *in_cols, int64_t
 /* in_cols[j]: host pointer to nrows bytes; counts: host uint64[k*256], overwritten */
 int lo_hist_u8_cols_host(lo_ctx *ctx, const uint8_t *const *in_cols, int64_t nrows, int32_t k,
                          uint64_t *counts, lo_host_timing *timing);
+
+/* ---- peer-memory histogram merge (multi-GPU, one process per GPU) -----------------------------------
+ * Instead of "local counts + all-reduce", every rank's fused kernel can flush its per-tile bin sums with
+ * RED.64 straight into ONE rank's count matrix over NVLink (spec.flags = LO_HIST_PEER_COUNTS): the merge
+ * is fused into the kernel's own flush and costs no extra pass.  These calls provide the plumbing:
+ * CUDA-IPC export/open of a device buffer and stream-ordered release/acquire flags.
+ * handle: 64 bytes (cudaIpcMemHandle_t).  lo_ipc_open must run in a DIFFERENT process than the export. */
+int lo_ipc_export(lo_ctx *ctx, void *dev_ptr, void *handle64);
+int lo_ipc_open(lo_ctx *ctx, const void *handle64, void **dev_ptr);
+int lo_ipc_close(lo_ctx *ctx, void *dev_ptr);
+/* raw device scratch (zeroed) for flags / shared count matrices */
+int lo_dev_alloc(lo_ctx *ctx, size_t bytes, void **dev_ptr);
+int lo_dev_free(lo_ctx *ctx, void *dev_ptr);
+/* after everything already enqueued on `stream`: fence (system scope) + release-add `inc` to *flag
+ * (flag may be peer memory) */
+int lo_flag_add_dev(lo_ctx *ctx, uint64_t *flag, uint64_t inc, void *stream);
+/* the same for up to 16 flags at once (one launch) */
+int lo_flag_add_many_dev(lo_ctx *ctx, uint64_t *const *flags, int32_t n, uint64_t inc, void *stream);
+int lo_dev_copy_dev(lo_ctx *ctx, void *dst, const void *src, size_t bytes, void *stream);
+/* make `stream` wait until *flag >= target (acquire, system scope).  Bounded: after timeout_ms the wait
+ * gives up and increments *timed_out_dev (device uint64) so a lost peer cannot hang the GPU. */
+int lo_flag_wait_dev(lo_ctx *ctx, const uint64_t *flag, uint64_t target, uint32_t timeout_ms,
+                     uint64_t *timed_out_dev, void *stream);
+int lo_dev_read_u64(lo_ctx *ctx, const uint64_t *dev_ptr, int64_t n, uint64_t *host, void *stream);
 
 /* Exact value counts of one dictionary-encoded column (R-semantics `$group`/`$sum:1`,
  * histogram_image/histogram.py:31-36, for columns with more than 256 distinct keys):

@@ -26,6 +26,7 @@ LO_ERR_ALIGNMENT = -6
 LO_F64, LO_F32, LO_U8, LO_U32 = 1, 2, 3, 4
 LO_SYNTH_UNIFORM, LO_SYNTH_EDGES, LO_SYNTH_CONSTCOL, LO_SYNTH_MNIST_U8 = 0, 1, 2, 3
 LO_MAX_BINS = 256
+LO_HIST_PEER_COUNTS = 1
 LO_ABI_VERSION = 1
 
 _ERR_NAMES = {
@@ -45,7 +46,7 @@ class LoexecError(RuntimeError):
 
 
 class HistSpec(C.Structure):
-    _fields_ = [("nbins", C.c_int32), ("reserved", C.c_int32),
+    _fields_ = [("nbins", C.c_int32), ("flags", C.c_int32),
                 ("lo", C.POINTER(C.c_float)), ("hi", C.POINTER(C.c_float))]
 
 
@@ -87,6 +88,16 @@ SIGNATURES = {
     "lo_project_cast_hist_host": (C.c_int, [_P, C.POINTER(_P), C.c_int64, C.c_int32, C.POINTER(_P),
                                             C.POINTER(HistSpec), _P, C.POINTER(HostTiming)]),
     "lo_hist_u8_cols_host": (C.c_int, [_P, C.POINTER(_P), C.c_int64, C.c_int32, _P, C.POINTER(HostTiming)]),
+    "lo_ipc_export": (C.c_int, [_P, _P, _P]),
+    "lo_ipc_open": (C.c_int, [_P, _P, C.POINTER(_P)]),
+    "lo_ipc_close": (C.c_int, [_P, _P]),
+    "lo_dev_alloc": (C.c_int, [_P, C.c_size_t, C.POINTER(_P)]),
+    "lo_dev_free": (C.c_int, [_P, _P]),
+    "lo_flag_add_dev": (C.c_int, [_P, _P, C.c_uint64, _P]),
+    "lo_flag_add_many_dev": (C.c_int, [_P, C.POINTER(_P), C.c_int32, C.c_uint64, _P]),
+    "lo_dev_copy_dev": (C.c_int, [_P, _P, _P, C.c_size_t, _P]),
+    "lo_flag_wait_dev": (C.c_int, [_P, _P, C.c_uint64, C.c_uint32, _P, _P]),
+    "lo_dev_read_u64": (C.c_int, [_P, _P, C.c_int64, _P, _P]),
     "lo_value_counts_u32_host": (C.c_int, [_P, _P, C.c_int64, C.c_uint32, _P, C.POINTER(HostTiming)]),
     "lo_minmax_cast_host": (C.c_int, [_P, C.POINTER(_P), C.c_int64, C.c_int32, _P, _P, _P, C.POINTER(HostTiming)]),
 }

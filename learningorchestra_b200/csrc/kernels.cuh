@@ -60,6 +60,8 @@ constexpr int kMaxColsU8    = 1024;
 struct ColsF64 {
     int32_t k;
     int32_t nbins;
+    int32_t sys_scope;   // 1: counts may live in a PEER GPU's memory -> RED.64 at system scope
+    int32_t pad_;
     int32_t col[kMaxColsF64];
     float   lo[kMaxColsF64];
     float   hi[kMaxColsF64];
@@ -194,7 +196,8 @@ __device__ __forceinline__ void zero_private(uint32_t *smem, int rows) {
 // Each private byte is <= 255 and a row holds kThreads = 256 words: a lane sums 8 words into
 // packed 16-bit halves (<= 2040), the 32-lane butterfly keeps them <= 65280 — no overflow.
 __device__ __forceinline__ void fold_and_flush(uint32_t *smem, int rows, int nbins,
-                                               unsigned long long *counts /* this column's bins */) {
+                                               unsigned long long *counts /* this column's bins */,
+                                               bool sys_scope = false) {
     uint32_t *folded = smem + kHistRows * kThreads;   // 256 words
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     __syncthreads();
@@ -222,7 +225,12 @@ __device__ __forceinline__ void fold_and_flush(uint32_t *smem, int rows, int nbi
     __syncthreads();
     if ((int)threadIdx.x < nbins) {
         uint32_t c = folded[threadIdx.x];
-        if (c) atomicAdd(counts + threadIdx.x, (unsigned long long)c);
+        if (c) {
+            // sys_scope: the count matrix is another GPU's memory mapped over NVLink (lo_ipc_open); the
+            // reduction is then performed by the owner's L2, i.e. the histogram merge rides on the flush
+            if (sys_scope) atomicAdd_system(counts + threadIdx.x, (unsigned long long)c);
+            else           atomicAdd(counts + threadIdx.x, (unsigned long long)c);
+        }
     }
 }
 
@@ -351,14 +359,52 @@ k_project_cast_hist(const char *__restrict__ in_base, long long in_pitch,
         }
     }
 
-    if (HIST) fold_and_flush(smem, rows, P.nbins, counts + (long long)j * P.nbins);
+    if (HIST) fold_and_flush(smem, rows, P.nbins, counts + (long long)j * P.nbins, P.sys_scope != 0);
 }
 
 // ---------------------------------------------------------------------------------------------
 // K4: per-column 256-bin value counts of byte columns
 // ---------------------------------------------------------------------------------------------
+#ifndef LO_U8_MODE
+#define LO_U8_MODE 2      // 0: bump4 per word   1: two bump2 per word   2: mode 1 + warp-uniform run fast path
+#endif
+
+// two increments with overlapped latencies (one compare instead of bump4's six)
+__device__ __forceinline__ void bump2(uint8_t *priv, uint32_t b0, uint32_t b1) {
+    uint8_t *p0 = priv + bin_byte_offset(b0), *p1 = priv + bin_byte_offset(b1);
+    uint32_t c0 = *p0, c1 = *p1;
+    c0 += 1;
+    c1 += 1 + (b1 == b0);
+    *p0 = (uint8_t)c0;
+    *p1 = (uint8_t)c1;
+}
+
 __device__ __forceinline__ void bump_word(uint8_t *priv, uint32_t x) {
+#if LO_U8_MODE == 0
     bump4(priv, (int)(x & 0xFFu), (int)((x >> 8) & 0xFFu), (int)((x >> 16) & 0xFFu), (int)(x >> 24));
+#else
+    bump2(priv, x & 0xFFu, (x >> 8) & 0xFFu);
+    bump2(priv, (x >> 16) & 0xFFu, x >> 24);
+#endif
+}
+
+// one 16-byte vector.  Run fast path: when every ACTIVE lane of the warp holds sixteen equal bytes
+// (constant columns: image borders, flags, padding) the whole vector is one counter += 16.  The vote
+// only keeps the branch warp-uniform (mixed data never executes both sides); correctness does not
+// depend on it, so it is taken over __activemask() — the ragged last tile runs with partial warps and a
+// full-mask vote there would wait forever for lanes that already left the loop.
+__device__ __forceinline__ void bump_vec16(uint8_t *priv, const uint4 &v) {
+#if LO_U8_MODE == 2
+    const uint32_t splat = __byte_perm(v.x, 0, 0x0000);
+    const bool run = (v.x == splat) & (v.y == splat) & (v.z == splat) & (v.w == splat);
+    if (__all_sync(__activemask(), run)) {
+        uint8_t *p = priv + bin_byte_offset(v.x & 0xFFu);
+        *p = (uint8_t)(*p + 16);
+        return;
+    }
+#endif
+    bump_word(priv, v.x); bump_word(priv, v.y);
+    bump_word(priv, v.z); bump_word(priv, v.w);
 }
 
 template <bool ALIGNED>
@@ -385,10 +431,7 @@ k_hist_u8_cols(const uint8_t *__restrict__ in_base, long long in_pitch, long lon
 #pragma unroll
                 for (int u = 0; u < kU8Batch; ++u) v[u] = ldg128_stream(in + e0 + (long long)u * kThreads * kU8VecBytes);
 #pragma unroll
-                for (int u = 0; u < kU8Batch; ++u) {
-                    bump_word(priv, v[u].x); bump_word(priv, v[u].y);
-                    bump_word(priv, v[u].z); bump_word(priv, v[u].w);
-                }
+                for (int u = 0; u < kU8Batch; ++u) bump_vec16(priv, v[u]);
             } else {
 #pragma unroll 1
                 for (int u = 0; u < kU8Batch; ++u) {
@@ -478,6 +521,36 @@ __global__ void k_fill_u8_mnist(uint8_t *base, long long pitch, long long nrows,
         uint8_t v = 0;
         if (py >= 4 && py < 24 && px >= 4 && px < 24 && (u & 0xFFu) >= 0x99u) v = (uint8_t)((u >> 8) & 0xFFu);
         base[(long long)c * pitch + r] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// cross-GPU flags for the peer-memory histogram merge (sharding.PeerReduce)
+// ---------------------------------------------------------------------------------------------
+// stream-ordered after the kernel whose REDs it publishes: fence, then release-add on a (peer) flag
+__global__ void k_flag_add(unsigned long long *flag, unsigned long long inc) {
+    __threadfence_system();
+    asm volatile("red.release.sys.global.add.u64 [%0], %1;" :: "l"(flag), "l"(inc) : "memory");
+}
+
+struct FlagPtrs { unsigned long long *p[16]; int n; };
+__global__ void k_flag_add_many(const __grid_constant__ FlagPtrs F, unsigned long long inc) {
+    __threadfence_system();
+    if ((int)threadIdx.x < F.n)
+        asm volatile("red.release.sys.global.add.u64 [%0], %1;" :: "l"(F.p[threadIdx.x]), "l"(inc) : "memory");
+}
+
+// spin until *flag >= target (acquire, system scope); gives up after ~timeout_ns and raises *timed_out
+__global__ void k_flag_wait(const unsigned long long *flag, unsigned long long target, unsigned long long timeout_ns,
+                            unsigned long long *timed_out) {
+    unsigned long long t0, now, v;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+        if (v >= target) return;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (now - t0 > timeout_ns) { atomicAdd(timed_out, 1ull); return; }
+        __nanosleep(200);
     }
 }
 

@@ -114,7 +114,7 @@ int check_cols(const lo_table *in, const int32_t *col_idx, int32_t k) {
 int check_spec(const lo_hist_spec *spec, int32_t k, float *w_out /* k */) {
     if (spec->nbins < 1 || spec->nbins > LO_MAX_BINS)
         return fail(LO_ERR_INVALID, "nbins = %d outside [1, %d]", spec->nbins, LO_MAX_BINS);
-    if (spec->reserved != 0) return fail(LO_ERR_INVALID, "lo_hist_spec.reserved must be 0");
+    if (spec->flags & ~LO_HIST_PEER_COUNTS) return fail(LO_ERR_INVALID, "unknown lo_hist_spec.flags 0x%x", spec->flags);
     if (!spec->lo || !spec->hi) return fail(LO_ERR_INVALID, "lo_hist_spec.lo / .hi is NULL");
     for (int j = 0; j < k; ++j) {
         const float lo = spec->lo[j], hi = spec->hi[j];
@@ -215,6 +215,8 @@ int project_cast_hist_impl(lo_ctx *ctx, const lo_table *in, const int32_t *col_i
         lo::ColsF64 P;
         P.k     = std::min<int32_t>(lo::kMaxColsF64, k - c0);
         P.nbins = spec ? spec->nbins : 0;
+        P.sys_scope = (spec && (spec->flags & LO_HIST_PEER_COUNTS)) ? 1 : 0;
+        P.pad_ = 0;
         for (int j = 0; j < P.k; ++j) {
             P.col[j] = col_idx[c0 + j];
             P.lo[j]  = spec ? spec->lo[c0 + j] : 0.f;
@@ -568,7 +570,7 @@ int lo_selftest_fastdiv(lo_ctx *ctx, float lo_v, float hi_v, int32_t nbins, int 
                         uint64_t *mismatches) {
     LO_TRY(check_ctx(ctx));
     if (!mismatches) return fail(LO_ERR_INVALID, "mismatches is NULL");
-    lo_hist_spec spec = {nbins, 0, &lo_v, &hi_v};
+    lo_hist_spec spec = {nbins, 0, &lo_v, &hi_v};   // flags = 0
     float w = 0.f;
     LO_TRY(check_spec(&spec, 1, &w));
     if (fast_path_used) *fast_path_used = fastdiv_ok(w) ? 1 : 0;
@@ -586,6 +588,98 @@ int lo_selftest_fastdiv(lo_ctx *ctx, float lo_v, float hi_v, int32_t nbins, int 
     cudaFree(d);
     if (e != cudaSuccess) return fail(LO_ERR_CUDA, "selftest: %s", cudaGetErrorString(e));
     *mismatches = h;
+    return LO_OK;
+}
+
+// ---- peer-memory merge plumbing ---------------------------------------------------------------------
+int lo_ipc_export(lo_ctx *ctx, void *dev_ptr, void *handle64) {
+    LO_TRY(check_ctx(ctx));
+    if (!dev_ptr || !handle64) return fail(LO_ERR_INVALID, "NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+    cudaIpcMemHandle_t h;
+    LO_CUDA(cudaIpcGetMemHandle(&h, dev_ptr));
+    memcpy(handle64, &h, 64);
+    return LO_OK;
+}
+
+int lo_ipc_open(lo_ctx *ctx, const void *handle64, void **dev_ptr) {
+    LO_TRY(check_ctx(ctx));
+    if (!dev_ptr || !handle64) return fail(LO_ERR_INVALID, "NULL argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    LO_CUDA(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return LO_OK;
+}
+
+int lo_ipc_close(lo_ctx *ctx, void *dev_ptr) {
+    LO_TRY(check_ctx(ctx));
+    if (dev_ptr) LO_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+    return LO_OK;
+}
+
+int lo_dev_alloc(lo_ctx *ctx, size_t bytes, void **dev_ptr) {
+    LO_TRY(check_ctx(ctx));
+    if (!dev_ptr || bytes == 0) return fail(LO_ERR_INVALID, "bad arguments");
+    LO_CUDA(cudaMalloc(dev_ptr, bytes));
+    LO_CUDA(cudaMemset(*dev_ptr, 0, bytes));
+    return LO_OK;
+}
+
+int lo_dev_free(lo_ctx *ctx, void *dev_ptr) {
+    LO_TRY(check_ctx(ctx));
+    if (dev_ptr) LO_CUDA(cudaFree(dev_ptr));
+    return LO_OK;
+}
+
+int lo_flag_add_dev(lo_ctx *ctx, uint64_t *flag, uint64_t inc, void *stream) {
+    LO_TRY(check_ctx(ctx));
+    if (!flag) return fail(LO_ERR_INVALID, "flag is NULL");
+    lo::k_flag_add<<<1, 1, 0, pick(ctx, stream)>>>((unsigned long long *)flag, inc);
+    LO_CUDA(cudaGetLastError());
+    ctx->launches.fetch_add(1, std::memory_order_relaxed);
+    return LO_OK;
+}
+
+int lo_flag_add_many_dev(lo_ctx *ctx, uint64_t *const *flags, int32_t n, uint64_t inc, void *stream) {
+    LO_TRY(check_ctx(ctx));
+    if (n < 0 || n > 16) return fail(LO_ERR_INVALID, "n must be in [0, 16]");
+    if (n == 0) return LO_OK;
+    if (!flags) return fail(LO_ERR_INVALID, "flags is NULL");
+    lo::FlagPtrs F;
+    F.n = n;
+    for (int i = 0; i < 16; ++i) F.p[i] = i < n ? (unsigned long long *)flags[i] : nullptr;
+    lo::k_flag_add_many<<<1, 32, 0, pick(ctx, stream)>>>(F, inc);
+    LO_CUDA(cudaGetLastError());
+    ctx->launches.fetch_add(1, std::memory_order_relaxed);
+    return LO_OK;
+}
+
+int lo_dev_copy_dev(lo_ctx *ctx, void *dst, const void *src, size_t bytes, void *stream) {
+    LO_TRY(check_ctx(ctx));
+    if (!dst || !src) return fail(LO_ERR_INVALID, "NULL argument");
+    LO_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, pick(ctx, stream)));
+    return LO_OK;
+}
+
+int lo_flag_wait_dev(lo_ctx *ctx, const uint64_t *flag, uint64_t target, uint32_t timeout_ms, uint64_t *timed_out_dev,
+                     void *stream) {
+    LO_TRY(check_ctx(ctx));
+    if (!flag || !timed_out_dev) return fail(LO_ERR_INVALID, "NULL argument");
+    if (timeout_ms == 0 || timeout_ms > 60000) return fail(LO_ERR_INVALID, "timeout_ms must be in [1, 60000]");
+    lo::k_flag_wait<<<1, 1, 0, pick(ctx, stream)>>>((const unsigned long long *)flag, target,
+                                                     (unsigned long long)timeout_ms * 1000000ull,
+                                                     (unsigned long long *)timed_out_dev);
+    LO_CUDA(cudaGetLastError());
+    ctx->launches.fetch_add(1, std::memory_order_relaxed);
+    return LO_OK;
+}
+
+int lo_dev_read_u64(lo_ctx *ctx, const uint64_t *dev_ptr, int64_t n, uint64_t *host, void *stream) {
+    LO_TRY(check_ctx(ctx));
+    if (!dev_ptr || !host || n <= 0) return fail(LO_ERR_INVALID, "bad arguments");
+    cudaStream_t s = pick(ctx, stream);
+    LO_CUDA(cudaMemcpyAsync(host, dev_ptr, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
+    LO_CUDA(cudaStreamSynchronize(s));
     return LO_OK;
 }
 

@@ -189,10 +189,10 @@ class Engine:
         return bool(used.value), int(bad.value)
 
     # ---- hot path, device resident ---------------------------------------------------------------
-    def _spec(self, k: int, nbins: int, lo, hi):
+    def _spec(self, k: int, nbins: int, lo, hi, flags: int = 0):
         lo_a = (C.c_float * k)(*[float(v) for v in np.broadcast_to(np.asarray(lo, dtype=np.float32), (k,))])
         hi_a = (C.c_float * k)(*[float(v) for v in np.broadcast_to(np.asarray(hi, dtype=np.float32), (k,))])
-        spec = N.HistSpec(int(nbins), 0, C.cast(lo_a, C.POINTER(C.c_float)), C.cast(hi_a, C.POINTER(C.c_float)))
+        spec = N.HistSpec(int(nbins), int(flags), C.cast(lo_a, C.POINTER(C.c_float)), C.cast(hi_a, C.POINTER(C.c_float)))
         return spec, (lo_a, hi_a)
 
     def project_cast(self, table: DeviceTable, col_idx, out: DeviceTable | None = None, out_dtype: str = "f32",
@@ -204,11 +204,11 @@ class Engine:
         return out
 
     def project_cast_hist(self, table: DeviceTable, col_idx, nbins: int, lo, hi, out: DeviceTable | None = None,
-                          counts: DeviceCounts | None = None, stream=None) -> DeviceCounts:
+                          counts: DeviceCounts | None = None, stream=None, peer_counts: bool = False) -> DeviceCounts:
         """Fused projection + cast + histogram; ``out=None`` computes the histogram only.
         ``counts`` is accumulated into (a fresh zeroed one is allocated when omitted)."""
         idx, k = _i32(col_idx)
-        spec, _keep = self._spec(k, nbins, lo, hi)
+        spec, _keep = self._spec(k, nbins, lo, hi, N.LO_HIST_PEER_COUNTS if peer_counts else 0)
         if counts is None:
             counts = self.counts(k, nbins)
         N.check(self._lib.lo_project_cast_hist_dev(self._ctx, table._h, idx, k, out._h if out is not None else None,
@@ -283,3 +283,48 @@ class Engine:
         N.check(self._lib.lo_minmax_cast_host(self._ctx, in_p, n, k, mins.ctypes.data_as(C.c_void_p),
                                               maxs.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.c_void_p), None))
         return mins, maxs, cnt
+
+    # ---- peer-memory plumbing (sharding.PeerReduce) ------------------------------------------------
+    def dev_alloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        N.check(self._lib.lo_dev_alloc(self._ctx, int(nbytes), C.byref(p)))
+        return int(p.value)
+
+    def dev_free(self, ptr: int) -> None:
+        N.check(self._lib.lo_dev_free(self._ctx, C.c_void_p(int(ptr))))
+
+    def ipc_export(self, ptr: int) -> bytes:
+        buf = C.create_string_buffer(64)
+        N.check(self._lib.lo_ipc_export(self._ctx, C.c_void_p(int(ptr)), buf))
+        return buf.raw
+
+    def ipc_open(self, handle: bytes) -> int:
+        p = C.c_void_p()
+        N.check(self._lib.lo_ipc_open(self._ctx, C.create_string_buffer(handle, 64), C.byref(p)))
+        return int(p.value)
+
+    def ipc_close(self, ptr: int) -> None:
+        N.check(self._lib.lo_ipc_close(self._ctx, C.c_void_p(int(ptr))))
+
+    def flag_add(self, flag_ptr: int, inc: int = 1, stream=None) -> None:
+        N.check(self._lib.lo_flag_add_dev(self._ctx, C.c_void_p(int(flag_ptr)), int(inc), _stream_ptr(stream)))
+
+    def flag_wait(self, flag_ptr: int, target: int, timed_out_ptr: int, timeout_ms: int = 2000, stream=None) -> None:
+        N.check(self._lib.lo_flag_wait_dev(self._ctx, C.c_void_p(int(flag_ptr)), int(target), int(timeout_ms),
+                                           C.c_void_p(int(timed_out_ptr)), _stream_ptr(stream)))
+
+    def read_u64(self, ptr: int, n: int = 1, stream=None) -> np.ndarray:
+        out = np.empty(int(n), dtype=np.uint64)
+        N.check(self._lib.lo_dev_read_u64(self._ctx, C.c_void_p(int(ptr)), int(n), out.ctypes.data_as(C.c_void_p),
+                                          _stream_ptr(stream)))
+        return out
+
+    def flag_add_many(self, flag_ptrs, inc: int = 1, stream=None) -> None:
+        arr = (C.c_void_p * len(flag_ptrs))(*[int(p) for p in flag_ptrs])
+        N.check(self._lib.lo_flag_add_many_dev(self._ctx, arr, len(flag_ptrs), int(inc), _stream_ptr(stream)))
+
+    def dev_copy(self, dst: int, src: int, nbytes: int, stream=None) -> None:
+        N.check(self._lib.lo_dev_copy_dev(self._ctx, C.c_void_p(int(dst)), C.c_void_p(int(src)), int(nbytes), _stream_ptr(stream)))
+
+    def dev_zero_u64(self, ptr: int, n: int, stream=None) -> None:
+        N.check(self._lib.lo_counts_zero_dev(self._ctx, C.c_void_p(int(ptr)), int(n), _stream_ptr(stream)))

@@ -1,5 +1,5 @@
 #!/bin/bash
 for f in learningorchestra_b200/lib/variants/libloexec_*.so; do
   echo "== $f"
-  LOEXEC_LIB=$PWD/$f python scripts/kbench.py 2>&1 | head -3
+  LOEXEC_LIB=$PWD/$f python scripts/kbench.py ${KB_ARGS:-} 2>&1 | grep -E "${KB_GREP:-.}"
 done
