@@ -189,6 +189,11 @@ int lo_dev_free(lo_ctx *ctx, void *dev_ptr);
 int lo_flag_add_dev(lo_ctx *ctx, uint64_t *flag, uint64_t inc, void *stream);
 /* the same for up to 16 flags at once (one launch) */
 int lo_flag_add_many_dev(lo_ctx *ctx, uint64_t *const *flags, int32_t n, uint64_t inc, void *stream);
+/* the root's whole per-step epilogue in one launch: wait *arrived >= target (bounded), move
+ * shared_counts[n] to result[n], re-zero shared_counts, release-add 1 to each peer's "clean" flag */
+int lo_peer_root_epilogue_dev(lo_ctx *ctx, const uint64_t *arrived, uint64_t target, uint32_t timeout_ms,
+                              uint64_t *timed_out_dev, uint64_t *shared_counts, uint64_t *result, int64_t n,
+                              uint64_t *const *peer_clean_flags, int32_t npeers, void *stream);
 int lo_dev_copy_dev(lo_ctx *ctx, void *dst, const void *src, size_t bytes, void *stream);
 /* make `stream` wait until *flag >= target (acquire, system scope).  Bounded: after timeout_ms the wait
  * gives up and increments *timed_out_dev (device uint64) so a lost peer cannot hang the GPU. */
@@ -202,6 +207,20 @@ int lo_dev_read_u64(lo_ctx *ctx, const uint64_t *dev_ptr, int64_t n, uint64_t *h
  * A code >= ncodes fails with LO_ERR_INVALID. */
 int lo_value_counts_u32_host(lo_ctx *ctx, const uint32_t *codes, int64_t nrows, uint32_t ncodes,
                              uint64_t *counts, lo_host_timing *timing);
+/* Text -> number for one column of cells: the reference's REAL cast, `float(document[field])` followed by
+ * `is_integer()` (data_type_handler_image/data_type_update.py:40-43), for every cell at once on the GPU.
+ * chars holds all cells back to back, cell i = chars[offsets[i] .. offsets[i+1]).  values[i] receives exactly
+ * the binary64 CPython's float() returns (correctly rounded; grammar incl. '_', inf, nan, whitespace).
+ * status[i]: LO_NUM_FLOAT 0 | LO_NUM_INTEGER 1 (integer valued: store int(v)) | LO_NUM_EMPTY 2 ("" -> None) |
+ * LO_NUM_INVALID 3 (float() raises ValueError) | LO_NUM_UNSUPPORTED 4 (non-ASCII byte or > 1024 bytes). */
+#define LO_NUM_FLOAT 0
+#define LO_NUM_INTEGER 1
+#define LO_NUM_EMPTY 2
+#define LO_NUM_INVALID 3
+#define LO_NUM_UNSUPPORTED 4
+int lo_parse_number_host(lo_ctx *ctx, const uint8_t *chars, const int64_t *offsets, int64_t n,
+                         double *values, uint8_t *status, lo_host_timing *timing);
+
 /* Per-column min and max of the CAST fp32 values over finite entries (NaN / +-inf ignored): the
  * range pre-pass for a histogram request that carries no range.
  * mins / maxs: host float[k]; nfinite: host uint64[k] (0 -> min = max = 0). */

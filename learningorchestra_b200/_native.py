@@ -27,6 +27,7 @@ LO_F64, LO_F32, LO_U8, LO_U32 = 1, 2, 3, 4
 LO_SYNTH_UNIFORM, LO_SYNTH_EDGES, LO_SYNTH_CONSTCOL, LO_SYNTH_MNIST_U8 = 0, 1, 2, 3
 LO_MAX_BINS = 256
 LO_HIST_PEER_COUNTS = 1
+LO_NUM_FLOAT, LO_NUM_INTEGER, LO_NUM_EMPTY, LO_NUM_INVALID, LO_NUM_UNSUPPORTED = 0, 1, 2, 3, 4
 LO_ABI_VERSION = 1
 
 _ERR_NAMES = {
@@ -95,10 +96,12 @@ SIGNATURES = {
     "lo_dev_free": (C.c_int, [_P, _P]),
     "lo_flag_add_dev": (C.c_int, [_P, _P, C.c_uint64, _P]),
     "lo_flag_add_many_dev": (C.c_int, [_P, C.POINTER(_P), C.c_int32, C.c_uint64, _P]),
+    "lo_peer_root_epilogue_dev": (C.c_int, [_P, _P, C.c_uint64, C.c_uint32, _P, _P, _P, C.c_int64, C.POINTER(_P), C.c_int32, _P]),
     "lo_dev_copy_dev": (C.c_int, [_P, _P, _P, C.c_size_t, _P]),
     "lo_flag_wait_dev": (C.c_int, [_P, _P, C.c_uint64, C.c_uint32, _P, _P]),
     "lo_dev_read_u64": (C.c_int, [_P, _P, C.c_int64, _P, _P]),
     "lo_value_counts_u32_host": (C.c_int, [_P, _P, C.c_int64, C.c_uint32, _P, C.POINTER(HostTiming)]),
+    "lo_parse_number_host": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P, C.POINTER(HostTiming)]),
     "lo_minmax_cast_host": (C.c_int, [_P, C.POINTER(_P), C.c_int64, C.c_int32, _P, _P, _P, C.POINTER(HostTiming)]),
 }
 

@@ -19,6 +19,7 @@
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+#include "parse_number.cuh"
 
 namespace lo {
 
@@ -554,6 +555,41 @@ __global__ void k_flag_wait(const unsigned long long *flag, unsigned long long t
     }
 }
 
+// root's whole epilogue of one peer-merge step in ONE launch: wait for all ranks' arrivals, move the merged
+// counts to the result buffer, re-zero the shared buffer, tell every peer it is clean again
+__global__ void k_peer_root_epilogue(const unsigned long long *arrived, unsigned long long target,
+                                     unsigned long long timeout_ns, unsigned long long *timed_out,
+                                     unsigned long long *shared_counts, unsigned long long *result, int n,
+                                     const __grid_constant__ FlagPtrs peers) {
+    __shared__ int ok;
+    if (threadIdx.x == 0) {
+        unsigned long long t0, now, v;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        ok = 1;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(arrived) : "memory");
+            if (v >= target) break;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (now - t0 > timeout_ns) { atomicAdd(timed_out, 1ull); ok = 0; break; }
+            __nanosleep(100);
+        }
+    }
+    __syncthreads();
+    if (ok) {
+        // the peers' REDs were performed by this GPU's L2; read them back there (bypass L1)
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            unsigned long long c;
+            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(c) : "l"(shared_counts + i) : "memory");
+            result[i] = c;
+            shared_counts[i] = 0ull;
+        }
+    }
+    __syncthreads();
+    __threadfence_system();
+    if ((int)threadIdx.x < peers.n)
+        asm volatile("red.release.sys.global.add.u64 [%0], %1;" :: "l"(peers.p[threadIdx.x]), "l"(1ull) : "memory");
+}
+
 // exact value counts of dictionary codes (R-semantics $group on arbitrary columns): RED.64 per element;
 // counts[ncodes] collects out-of-range codes so the host can reject them
 __global__ void k_count_codes_u32(const uint32_t *__restrict__ codes, long long n, uint32_t ncodes,
@@ -596,6 +632,21 @@ __global__ void k_minmax_cast(const char *__restrict__ base, long long pitch, lo
         atomicMax(out + 3 * blockIdx.y + 0, (unsigned long long)mn);
         atomicMax(out + 3 * blockIdx.y + 1, (unsigned long long)mx);
         atomicAdd(out + 3 * blockIdx.y + 2, cnt);
+    }
+}
+
+// R-semantics cast "number" (data_type_update.py:40-43): one cell per thread, CPython float() grammar,
+// correctly rounded binary64 (parse_number.cuh) + the is_integer() flag the adapter turns into int(v)
+__global__ void k_parse_number(const uint8_t *__restrict__ chars, const long long *__restrict__ offsets, long long n,
+                               unsigned long long *__restrict__ value_bits, uint8_t *__restrict__ status) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long b = offsets[i], e = offsets[i + 1];
+        uint64_t bits = 0;
+        const long long len = e - b;
+        uint8_t st = (len < 0 || len > num::kMaxLen) ? (uint8_t)num::kUnsupported
+                                                     : num::parse_number(chars + b, (int)len, bits);
+        value_bits[i] = bits;
+        status[i] = st;
     }
 }
 

@@ -654,6 +654,25 @@ int lo_flag_add_many_dev(lo_ctx *ctx, uint64_t *const *flags, int32_t n, uint64_
     return LO_OK;
 }
 
+int lo_peer_root_epilogue_dev(lo_ctx *ctx, const uint64_t *arrived, uint64_t target, uint32_t timeout_ms,
+                              uint64_t *timed_out_dev, uint64_t *shared_counts, uint64_t *result, int64_t n,
+                              uint64_t *const *peer_clean_flags, int32_t npeers, void *stream) {
+    LO_TRY(check_ctx(ctx));
+    if (!arrived || !timed_out_dev || !shared_counts || !result || n <= 0 || n > 0x7fffffff)
+        return fail(LO_ERR_INVALID, "bad arguments");
+    if (npeers < 0 || npeers > 16 || (npeers > 0 && !peer_clean_flags)) return fail(LO_ERR_INVALID, "npeers must be in [0, 16]");
+    if (timeout_ms == 0 || timeout_ms > 60000) return fail(LO_ERR_INVALID, "timeout_ms must be in [1, 60000]");
+    lo::FlagPtrs F;
+    F.n = npeers;
+    for (int i = 0; i < 16; ++i) F.p[i] = i < npeers ? (unsigned long long *)peer_clean_flags[i] : nullptr;
+    lo::k_peer_root_epilogue<<<1, 1024, 0, pick(ctx, stream)>>>(
+        (const unsigned long long *)arrived, target, (unsigned long long)timeout_ms * 1000000ull,
+        (unsigned long long *)timed_out_dev, (unsigned long long *)shared_counts, (unsigned long long *)result, (int)n, F);
+    LO_CUDA(cudaGetLastError());
+    ctx->launches.fetch_add(1, std::memory_order_relaxed);
+    return LO_OK;
+}
+
 int lo_dev_copy_dev(lo_ctx *ctx, void *dst, const void *src, size_t bytes, void *stream) {
     LO_TRY(check_ctx(ctx));
     if (!dst || !src) return fail(LO_ERR_INVALID, "NULL argument");
@@ -871,6 +890,58 @@ int lo_value_counts_u32_host(lo_ctx *ctx, const uint32_t *codes, int64_t nrows, 
     LO_TRY(rc);
     if (tmp[ncodes] != 0) return fail(LO_ERR_INVALID, "%llu codes were >= ncodes (%u)", (unsigned long long)tmp[ncodes], ncodes);
     memcpy(counts, tmp.data(), (size_t)ncodes * 8);
+    return LO_OK;
+}
+
+// text -> number for one column of cells (R-semantics "number" cast).  chars: all cells back to back;
+// offsets[i] .. offsets[i+1] delimit cell i.  values[i] = the binary64 CPython's float() returns,
+// status[i] in {0 float, 1 integer-valued, 2 empty string, 3 invalid (ValueError), 4 not decidable on device}.
+int lo_parse_number_host(lo_ctx *ctx, const uint8_t *chars, const int64_t *offsets, int64_t n, double *values,
+                         uint8_t *status, lo_host_timing *timing) {
+    LO_TRY(check_ctx(ctx));
+    if (n < 0) return fail(LO_ERR_INVALID, "n < 0");
+    if (n == 0) return LO_OK;
+    if (!offsets || !values || !status) return fail(LO_ERR_INVALID, "NULL argument");
+    const int64_t nbytes = offsets[n] - offsets[0];
+    if (nbytes < 0 || (nbytes > 0 && !chars)) return fail(LO_ERR_INVALID, "bad offsets / chars");
+    for (int64_t i = 0; i < n; ++i)
+        if (offsets[i + 1] < offsets[i]) return fail(LO_ERR_INVALID, "offsets must be non-decreasing (row %lld)", (long long)i);
+    const auto t0 = std::chrono::steady_clock::now();
+    const int64_t launches0 = ctx->launches.load();
+    uint8_t *d_chars = nullptr, *d_status = nullptr;
+    long long *d_off = nullptr;
+    unsigned long long *d_val = nullptr;
+    cudaStream_t s = ctx->stream;
+    cudaError_t e = cudaMalloc((void **)&d_chars, (size_t)std::max<int64_t>(nbytes, 1));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_off, (size_t)(n + 1) * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_val, (size_t)n * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_status, (size_t)n);
+    if (e == cudaSuccess && nbytes) e = cudaMemcpyAsync(d_chars, chars + offsets[0], (size_t)nbytes, cudaMemcpyHostToDevice, s);
+    std::vector<int64_t> rel;
+    const int64_t *off_src = offsets;
+    if (e == cudaSuccess && offsets[0] != 0) {
+        rel.resize(n + 1);
+        for (int64_t i = 0; i <= n; ++i) rel[i] = offsets[i] - offsets[0];
+        off_src = rel.data();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_off, off_src, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) {
+        const int grid = (int)std::min<int64_t>((n + 127) / 128, (int64_t)ctx->sm_count * 16);
+        lo::k_parse_number<<<grid, 128, 0, s>>>(d_chars, d_off, n, d_val, d_status);
+        e = cudaGetLastError();
+        ctx->launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(values, d_val, (size_t)n * 8, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(status, d_status, (size_t)n, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaFree(d_chars); cudaFree(d_off); cudaFree(d_val); cudaFree(d_status);
+    if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? LO_ERR_NOMEM : LO_ERR_CUDA, "parse_number: %s", cudaGetErrorString(e));
+    if (timing) {
+        timing->total_ms  = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        timing->h2d_bytes = (double)nbytes + (double)(n + 1) * 8;
+        timing->d2h_bytes = (double)n * 9;
+        timing->launches  = ctx->launches.load() - launches0;
+    }
     return LO_OK;
 }
 

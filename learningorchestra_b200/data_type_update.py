@@ -1,11 +1,16 @@
 """``DataType`` — drop-in for ``data_type_handler_image/data_type_update.py`` (same constructor and
 methods, in-place conversion of the input collection, same ``finished`` False -> True protocol).
 
-* ``"string"`` / ``"number"`` (the reference's types): text <-> number conversion of Python objects —
-  ``float(str)`` with the integer collapse, ``str(v)`` — is format conversion in the document adapter
-  and runs on the host exactly as the reference's lines do (``data_type_update.py:22-43``, dead
-  ``== str/int/float`` checks included).  Moving the decimal parse to the GPU is the first "next" row
-  (SURVEY.md §8f rank 1); it is not wired in yet and nothing pretends otherwise.
+* ``"number"`` (``data_type_update.py:30-43``): every text cell of the field is parsed ON THE GPU
+  (``lo_parse_number_host`` -> ``k_parse_number``: CPython ``float()`` grammar, correctly rounded binary64,
+  plus the ``is_integer()`` flag) — the reference does ``float(document[field])`` one document at a time.
+  The adapter keeps the reference's branch order around it: ``None`` untouched, ``""`` -> ``None``, the dead
+  ``== int / == float`` checks, integer-valued results stored as ``int``; an unparsable cell raises
+  ``ValueError`` after the earlier documents were updated, so the collection is left exactly as the
+  reference leaves it (``finished: False``).  Cells with non-ASCII bytes or > 1024 bytes are not decided on
+  the device and fail the job loudly (no host ``float()`` fallback).
+* ``"string"`` (``data_type_update.py:22-28``): ``str(v)`` / ``None -> ""`` is text formatting of Python
+  objects in the document adapter and stays on the host (out of the GPU's scope).
 * ``"float32"`` (this build's optional extension): the B-semantics cast of SURVEY.md §0 — numeric values
   go through the sm_100a kernel (fp64 -> fp32 round-to-nearest-even) and are stored back widened.
 """
@@ -36,8 +41,11 @@ class DataType:
     def field_converter(self, filename, field, field_type):
         documents = columnar.data_rows(self.database_connector.find(filename, {}))
         updates = {}
+        failure = None
         if field_type == self.FLOAT32_TYPE:
             updates = self.__gpu_float32(documents, field)
+        elif field_type == self.NUMBER_TYPE:
+            updates, failure = self.__gpu_number(documents, field)
         else:
             for document in documents:
                 values = {}
@@ -48,18 +56,43 @@ class DataType:
                         values[field] = ""
                     else:
                         values[field] = str(document[field])
-                elif field_type == self.NUMBER_TYPE:
-                    if document[field] == int or document[field] == float or document[field] is None:
-                        continue
-                    if document[field] == "":
-                        values[field] = None
-                    else:
-                        values[field] = float(document[field])
-                        if values[field].is_integer():
-                            values[field] = int(values[field])
                 if values:
                     updates[document[self.DOCUMENT_ID_NAME]] = values
         self.database_connector.update_by_id(filename, updates)
+        if failure is not None:
+            raise failure
+
+    def __gpu_number(self, documents, field):
+        """``data_type_update.py:30-43`` with the ``float(str)`` of every text cell done by the GPU parser."""
+        if self.engine is None:
+            raise RuntimeError("type 'number' parses text on the GPU and needs an Engine (there is no CPU fallback)")
+        from . import _native as N
+        text_rows = [i for i, d in enumerate(documents) if isinstance(d[field], str) and d[field] != ""]
+        parsed, status = self.engine.parse_number_host([documents[i][field] for i in text_rows])
+        where = {row: j for j, row in enumerate(text_rows)}
+        updates = {}
+        for i, document in enumerate(documents):
+            value = document[field]
+            if value == int or value == float or value is None:       # :32-36 (first two never true)
+                continue
+            if value == "":
+                new = None
+            elif i in where:
+                j = where[i]
+                if status[j] == N.LO_NUM_INVALID:
+                    return updates, ValueError(f"could not convert string to float: {value!r}")
+                if status[j] == N.LO_NUM_UNSUPPORTED:
+                    return updates, RuntimeError(f"cell {value[:40]!r} (non-ASCII or > 1024 bytes) is not parsed on the "
+                                                 "device and there is no CPU fallback")
+                new = float(parsed[j])
+                if status[j] == N.LO_NUM_INTEGER:
+                    new = int(new)
+            else:                                                        # already a number (or bool): no text to parse
+                new = float(value)
+                if new.is_integer():
+                    new = int(new)
+            updates[document[self.DOCUMENT_ID_NAME]] = {field: new}
+        return updates, None
 
     def __gpu_float32(self, documents, field):
         if self.engine is None:

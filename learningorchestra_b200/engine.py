@@ -328,3 +328,26 @@ class Engine:
 
     def dev_zero_u64(self, ptr: int, n: int, stream=None) -> None:
         N.check(self._lib.lo_counts_zero_dev(self._ctx, C.c_void_p(int(ptr)), int(n), _stream_ptr(stream)))
+
+    def peer_root_epilogue(self, arrived_ptr: int, target: int, timed_out_ptr: int, shared_counts: int, result: int,
+                           n: int, peer_clean_ptrs, timeout_ms: int = 2000, stream=None) -> None:
+        arr = (C.c_void_p * max(len(peer_clean_ptrs), 1))(*[int(p) for p in peer_clean_ptrs])
+        N.check(self._lib.lo_peer_root_epilogue_dev(self._ctx, C.c_void_p(int(arrived_ptr)), int(target), int(timeout_ms),
+                                                    C.c_void_p(int(timed_out_ptr)), C.c_void_p(int(shared_counts)),
+                                                    C.c_void_p(int(result)), int(n), arr, len(peer_clean_ptrs),
+                                                    _stream_ptr(stream)))
+
+    def parse_number_host(self, cells):
+        """cells: list of ``str`` / ``bytes``.  Returns (values float64[n], status uint8[n]) — values are what
+        CPython's ``float(cell)`` returns, status as LO_NUM_* (``_native``)."""
+        enc = [c.encode("utf-8") if isinstance(c, str) else bytes(c) for c in cells]
+        n = len(enc)
+        offsets = np.zeros(n + 1, dtype=np.int64)
+        if n:
+            np.cumsum([len(b) for b in enc], out=offsets[1:])
+        chars = np.frombuffer(b"".join(enc) + b"\0", dtype=np.uint8)
+        values = np.zeros(n, dtype=np.float64)
+        status = np.zeros(n, dtype=np.uint8)
+        N.check(self._lib.lo_parse_number_host(self._ctx, chars.ctypes.data_as(C.c_void_p), offsets.ctypes.data_as(C.c_void_p),
+                                               n, values.ctypes.data_as(C.c_void_p), status.ctypes.data_as(C.c_void_p), None))
+        return values, status

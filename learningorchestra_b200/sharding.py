@@ -117,12 +117,10 @@ class PeerReduce:
         eng.flag_add(self.root_flags + self._ARRIVED + 8 * parity, 1, stream)    # arrived[parity] += 1 on the root
         if self.rank == self.root:
             buf = self.counts_base + parity * self.n * 8
-            eng.flag_wait(self.flags + self._ARRIVED + 8 * parity, self.world * (self.step // 2 + 1),
-                          self.flags + self._TIMED_OUT, self.timeout_ms, stream)
-            eng.dev_copy(self.result, buf, self.n * 8, stream)
-            eng.dev_zero_u64(buf, self.n, stream)
-            if self.peer_clean:
-                eng.flag_add_many(self.peer_clean, 1, stream)
+            # one launch: wait for W arrivals, move the merged counts to `result`, re-zero, signal "clean"
+            eng.peer_root_epilogue(self.flags + self._ARRIVED + 8 * parity, self.world * (self.step // 2 + 1),
+                                   self.flags + self._TIMED_OUT, buf, self.result, self.n, self.peer_clean,
+                                   self.timeout_ms, stream)
         self.step += 1
 
     # -- results ----------------------------------------------------------------------------------------

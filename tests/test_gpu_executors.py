@@ -55,6 +55,82 @@ def test_titanic_histogram_value_counts_match_reference_execution(engine):
         assert rsem.normalise_group_result(mine[f]) == rsem.normalise_group_result(theirs[f]), f
 
 
+def test_number_cast_on_gpu_matches_reference_execution(engine):
+    """PATCH /fieldTypes "number": every text cell parsed by k_parse_number == the reference's float()+collapse."""
+    import math
+    db = _titanic_db()
+    gold = _load("reference_datatype_number.json")
+    job = DataType(db, utils.DataTypeMetadata(db), engine)
+    job.convert_existent_file("titanic", {f: "number" for f in gold["fields"]})
+    job.wait()
+    assert db.find_one("titanic", {"_id": 0})["finished"] is True
+    got = sorted(([d["_id"]] + [d[f] for f in gold["fields"]] for d in db.find("titanic", {}) if d["_id"] != 0))
+    assert len(got) == 891
+    for a, b in zip(got, gold["rows"]):
+        assert all(type(x) is type(y) and x == y for x, y in zip(a, b)), (a, b)
+    # the per-value vectors of SURVEY.md §8c, produced by the reference's own converter
+    vec = _load("reference_cast_vectors.json")
+    vdb = utils.Database()
+    vdb.insert_one_in_file("vec", rsem.dataset_metadata("vec", ["v"]))
+    vdb.insert_many_in_file("vec", [{"_id": i + 1, "v": v} for i, v in enumerate(vec["in"])])
+    job = DataType(vdb, utils.DataTypeMetadata(vdb), engine)
+    job.convert_existent_file("vec", {"v": "number"})
+    job.wait()
+    out = [d["v"] for d in sorted(vdb.find("vec", {}), key=lambda d: d["_id"]) if d["_id"] != 0]
+    for s_in, g, want in zip(vec["in"], out, vec["number"]):
+        if isinstance(want, dict) and "float" in want:
+            w = float(want["float"])
+            assert isinstance(g, float) and (g == w or (math.isnan(g) and math.isnan(w))), (s_in, g, want)
+        elif isinstance(want, dict):
+            assert isinstance(g, int) and g == int(want["int"]), (s_in, g, want)
+        else:
+            assert g is None and want is None
+    # an unparsable cell: earlier documents converted, job fails, finished stays False (reference behaviour)
+    bdb = utils.Database()
+    bdb.insert_one_in_file("b", rsem.dataset_metadata("b", ["v"]))
+    bdb.insert_many_in_file("b", [{"_id": 1, "v": "1.5"}, {"_id": 2, "v": "abc"}, {"_id": 3, "v": "2"}])
+    job = DataType(bdb, utils.DataTypeMetadata(bdb), engine)
+    job.convert_existent_file("b", {"v": "number"})
+    with pytest.raises(ValueError, match="could not convert string to float: 'abc'"):
+        job.wait()
+    assert [d["v"] for d in sorted(bdb.find("b", {}), key=lambda d: d["_id"]) if d["_id"]] == [1.5, "abc", "2"]
+    assert bdb.find_one("b", {"_id": 0})["finished"] is False
+
+
+def test_gpu_parser_equals_python_float_on_random_text(engine):
+    import random
+    import struct
+    rng = random.Random(99)
+    cells = []
+    for _ in range(200_000):
+        k = rng.random()
+        if k < 0.4:
+            cells.append(repr(struct.unpack("<d", struct.pack("<Q", rng.getrandbits(64) & 0x7FEFFFFFFFFFFFFF))[0]))
+        elif k < 0.6:
+            cells.append(f"{rng.uniform(-1e4, 1e4):.{rng.randint(0, 12)}f}")
+        elif k < 0.8:
+            cells.append(str(rng.randint(-10 ** 12, 10 ** 12)))
+        elif k < 0.9:
+            d = "".join(rng.choice("0123456789") for _ in range(rng.randint(20, 40)))
+            cells.append(d[:7] + "." + d[7:] + f"e{rng.randint(-300, 280)}")
+        else:
+            cells.append(rng.choice(["", " 5 ", "1_000", "nan", "-inf", "abc", "1e", "0x10", "１２", "+.5", "1.e3", "-0.0", "1e400"]))
+    vals, st = engine.parse_number_host(cells)
+    for c, v, t in zip(cells, vals, st):
+        if c == "":
+            assert t == 2
+        elif any(ord(ch) > 127 for ch in c):
+            assert t == 4
+        else:
+            try:
+                w = float(c)
+            except ValueError:
+                assert t == 3, c
+                continue
+            assert t == (1 if (w == w and abs(w) != float("inf") and w.is_integer()) else 0), (c, t)
+            assert (v == w and np.signbit(v) == np.signbit(w)) or (v != v and w != w), (c, v, w)
+
+
 def test_byte_table_value_counts_match_reference_execution(engine):
     """Config M bridge: on byte columns the 256-bin histogram IS the reference's $group output."""
     gold = _load("reference_histogram_bytes.json")

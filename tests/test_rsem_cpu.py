@@ -98,35 +98,31 @@ def test_oracle_select_is_keyed_by_id():
 
 
 # ---- (2) product host logic vs the goldens ----------------------------------------------------------------
-def test_product_datatype_matches_reference_execution():
+def test_product_datatype_string_branch_matches_reference_execution():
+    """number -> string is host-side text formatting (a5); checked from the reference's own converted rows."""
     db = utils.Database()
-    _titanic_db(db)
-    gold = _load("reference_datatype_number.json")
+    gold_n, gold_s = _load("reference_datatype_number.json"), _load("reference_datatype_string.json")
+    db.insert_one_in_file("t", rsem.dataset_metadata("t", gold_n["fields"]))
+    db.insert_many_in_file("t", [dict(zip(["_id"] + gold_n["fields"], row)) for row in gold_n["rows"]])
     job = DataType(db, utils.DataTypeMetadata(db))
-    job.convert_existent_file("titanic", {f: "number" for f in gold["fields"]})
+    job.convert_existent_file("t", {"Age": "string", "Survived": "string"})
     job.wait()
-    assert db.find_one("titanic", {"_id": 0})["finished"] is True
-    got = sorted(([d["_id"]] + [d[f] for f in gold["fields"]] for d in db.find("titanic", {}) if d["_id"] != 0))
-    for a, b in zip(got, gold["rows"]):
-        assert all(_same(x, y) for x, y in zip(a, b)), (a, b)
-    gold_s = _load("reference_datatype_string.json")
-    job = DataType(db, utils.DataTypeMetadata(db))
-    job.convert_existent_file("titanic", {"Age": "string", "Survived": "string"})
-    job.wait()
-    got = sorted([d["_id"], d["Age"], d["Survived"]] for d in db.find("titanic", {}) if d["_id"] != 0)
+    assert db.find_one("t", {"_id": 0})["finished"] is True
+    got = sorted([d["_id"], d["Age"], d["Survived"]] for d in db.find("t", {}) if d["_id"] != 0)
     assert got == gold_s["rows"]
 
 
-def test_product_datatype_bad_text_leaves_unfinished():
+def test_product_datatype_number_needs_the_gpu():
     db = utils.Database()
     db.insert_one_in_file("t", rsem.dataset_metadata("t", ["v"]))
-    db.insert_one_in_file("t", {"_id": 1, "v": "abc"})
-    job = DataType(db, utils.DataTypeMetadata(db))
+    db.insert_one_in_file("t", {"_id": 1, "v": "12"})
+    job = DataType(db, utils.DataTypeMetadata(db))          # no engine
     job.convert_existent_file("t", {"v": "number"})
-    with pytest.raises(ValueError):
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
         job.wait()
     meta = db.find_one("t", {"_id": 0})
-    assert meta["finished"] is False and "ValueError" in meta["exception"]
+    assert meta["finished"] is False and "no CPU fallback" in meta["exception"]
+    assert db.find_one("t", {"_id": 1})["v"] == "12"       # untouched
 
 
 def test_product_projection_select_matches_oracle():
@@ -185,12 +181,12 @@ def test_rest_success_bodies_and_reader():
     r = c.post("/projections", json={"inputDatasetName": "titanic", "outputDatasetName": "p1", "names": ["Age", "Fare"]})
     assert r.status_code == 201
     assert r.get_json() == {"result": "/api/learningOrchestra/v1/transform/projection/p1?query={}&limit=20&skip=0"}
-    r = c.patch("/fieldTypes", json={"inputDatasetName": "p1", "types": {"Age": "number", "Fare": "number"}})
+    r = c.patch("/fieldTypes", json={"inputDatasetName": "p1", "types": {"Age": "string", "Fare": "string"}})
     assert r.status_code == 200
     assert r.get_json() == {"result": "/api/learningOrchestra/v1/dataset/p1?query={}&limit=20&skip=0"}
     page = c.get("/files/p1?skip=0&limit=3&query={}").get_json()["result"]
     assert [d["_id"] for d in page] == [0, 1, 2] and page[0]["finished"] is True
-    assert isinstance(page[1]["Fare"], (int, float))
+    assert isinstance(page[1]["Fare"], str)
     assert len(c.get("/files/p1?limit=1000").get_json()["result"]) == 100       # limit capped at 100
     # POST /histograms answers 201 at once (async protocol); with no GPU the job itself must fail loudly
     r = c.post("/histograms", json={"inputDatasetName": "p1", "outputDatasetName": "h1", "names": ["Age"]})
