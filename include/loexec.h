@@ -207,6 +207,14 @@ int lo_dev_read_u64(lo_ctx *ctx, const uint64_t *dev_ptr, int64_t n, uint64_t *h
  * A code >= ncodes fails with LO_ERR_INVALID. */
 int lo_value_counts_u32_host(lo_ctx *ctx, const uint32_t *codes, int64_t nrows, uint32_t ncodes,
                              uint64_t *counts, lo_host_timing *timing);
+/* Exact value counts of one NUMERIC column without a host dictionary (GPU hash group-by): keys are
+ * compared with MongoDB's `$group` equality for numbers (-0.0 == 0.0 -> key +0.0, every NaN -> one NaN key).
+ * keys_out / counts_out: host arrays of `capacity` entries, filled in unspecified order (as `$group`);
+ * *ndistinct = number of groups.  More groups than capacity -> LO_ERR_INVALID (ndistinct still set). */
+int lo_value_counts_f64_host(lo_ctx *ctx, const double *values, int64_t n, double *keys_out,
+                             uint64_t *counts_out, int64_t capacity, int64_t *ndistinct,
+                             lo_host_timing *timing);
+
 /* Text -> number for one column of cells: the reference's REAL cast, `float(document[field])` followed by
  * `is_integer()` (data_type_handler_image/data_type_update.py:40-43), for every cell at once on the GPU.
  * chars holds all cells back to back, cell i = chars[offsets[i] .. offsets[i+1]).  values[i] receives exactly

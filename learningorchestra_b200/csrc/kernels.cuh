@@ -635,6 +635,55 @@ __global__ void k_minmax_cast(const char *__restrict__ base, long long pitch, lo
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// exact value counts of a numeric column without a host dictionary: GPU hash group-by
+// ($group / $sum:1 of histogram_image/histogram.py:31-36 on number fields).  Keys are binary64 bit patterns
+// canonicalised to MongoDB's grouping equality for numbers (-0.0 == 0.0, NaN == NaN); open addressing with
+// linear probing in HBM, 64-bit CAS to claim a slot, RED.64 to count; equal keys inside a warp are merged
+// first (match.any) so a two-valued column does not serialise on two L2 addresses.
+// ---------------------------------------------------------------------------------------------
+constexpr unsigned long long kEmptyKey = 0xFFFFFFFFFFFFFFFFull;      // a NaN payload no canonical key can have
+
+__device__ __forceinline__ unsigned long long canonical_key(double x) {
+    if (x != x) return 0x7FF8000000000000ull;
+    if (x == 0.0) return 0ull;
+    return (unsigned long long)__double_as_longlong(x);
+}
+
+__global__ void k_hash_count_f64(const double *__restrict__ values, long long n, unsigned long long *__restrict__ keys,
+                                 unsigned long long *__restrict__ counts, unsigned long long mask) {
+    for (long long i0 = blockIdx.x * (long long)blockDim.x; i0 < n; i0 += (long long)gridDim.x * blockDim.x) {
+        const long long i = i0 + threadIdx.x;
+        const bool live = i < n;
+        const unsigned active = __ballot_sync(0xffffffffu, live);
+        if (!live) continue;
+        const unsigned long long key = canonical_key(values[i]);
+        const unsigned peers = __match_any_sync(active, key);
+        if ((int)(threadIdx.x & 31) != __ffs(peers) - 1) continue;      // one lane per distinct key in the warp
+        const unsigned long long add = (unsigned long long)__popc(peers);
+        unsigned long long h = splitmix64(key) & mask;
+        for (;;) {
+            const unsigned long long old = atomicCAS(keys + h, kEmptyKey, key);
+            if (old == kEmptyKey || old == key) { atomicAdd(counts + h, add); break; }
+            h = (h + 1) & mask;
+        }
+    }
+}
+
+__global__ void k_hash_compact(const unsigned long long *__restrict__ keys, const unsigned long long *__restrict__ counts,
+                               unsigned long long slots, unsigned long long *__restrict__ out_keys,
+                               unsigned long long *__restrict__ out_counts, unsigned long long capacity,
+                               unsigned long long *__restrict__ n_out) {
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < slots;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long k = keys[i];
+        if (k != kEmptyKey) {
+            const unsigned long long pos = atomicAdd(n_out, 1ull);
+            if (pos < capacity) { out_keys[pos] = k; out_counts[pos] = counts[i]; }
+        }
+    }
+}
+
 // R-semantics cast "number" (data_type_update.py:40-43): one cell per thread, CPython float() grammar,
 // correctly rounded binary64 (parse_number.cuh) + the is_integer() flag the adapter turns into int(v)
 __global__ void k_parse_number(const uint8_t *__restrict__ chars, const long long *__restrict__ offsets, long long n,

@@ -893,6 +893,61 @@ int lo_value_counts_u32_host(lo_ctx *ctx, const uint32_t *codes, int64_t nrows, 
     return LO_OK;
 }
 
+// exact value counts of one numeric column (GPU hash group-by).  keys_out / counts_out: host arrays of
+// `capacity` entries; *ndistinct receives the number of distinct keys (may exceed capacity: then only the first
+// `capacity` groups were written and the call fails with LO_ERR_INVALID so the caller can retry larger).
+int lo_value_counts_f64_host(lo_ctx *ctx, const double *values, int64_t n, double *keys_out, uint64_t *counts_out,
+                             int64_t capacity, int64_t *ndistinct, lo_host_timing *timing) {
+    LO_TRY(check_ctx(ctx));
+    if (n < 0 || capacity < 0) return fail(LO_ERR_INVALID, "negative size");
+    if (!ndistinct) return fail(LO_ERR_INVALID, "ndistinct is NULL");
+    *ndistinct = 0;
+    if (n == 0) return LO_OK;
+    if (!values || (capacity > 0 && (!keys_out || !counts_out))) return fail(LO_ERR_INVALID, "NULL argument");
+    const auto t0 = std::chrono::steady_clock::now();
+    const int64_t launches0 = ctx->launches.load();
+    unsigned long long slots = 1024;
+    while (slots < 2ull * (unsigned long long)n) slots <<= 1;
+    double *d_val = nullptr;
+    unsigned long long *d_keys = nullptr, *d_counts = nullptr, *d_out = nullptr;
+    const size_t out_n = (size_t)std::max<int64_t>(capacity, 1);
+    cudaStream_t s = ctx->stream;
+    cudaError_t e = cudaMalloc((void **)&d_val, (size_t)n * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_keys, slots * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_counts, slots * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_out, (2 * out_n + 1) * 8);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_val, values, (size_t)n * 8, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_keys, 0xFF, slots * 8, s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_counts, 0, slots * 8, s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_out + 2 * out_n, 0, 8, s);
+    if (e == cudaSuccess) {
+        const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 8);
+        lo::k_hash_count_f64<<<grid, 256, 0, s>>>(d_val, n, d_keys, d_counts, slots - 1);
+        lo::k_hash_compact<<<ctx->sm_count * 8, 256, 0, s>>>(d_keys, d_counts, slots, d_out, d_out + out_n,
+                                                              (unsigned long long)capacity, d_out + 2 * out_n);
+        e = cudaGetLastError();
+        ctx->launches.fetch_add(2, std::memory_order_relaxed);
+    }
+    unsigned long long nd = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&nd, d_out + 2 * out_n, 8, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    const size_t take = (size_t)std::min<unsigned long long>(nd, (unsigned long long)capacity);
+    if (e == cudaSuccess && take) e = cudaMemcpy(keys_out, d_out, take * 8, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && take) e = cudaMemcpy(counts_out, d_out + out_n, take * 8, cudaMemcpyDeviceToHost);
+    cudaFree(d_val); cudaFree(d_keys); cudaFree(d_counts); cudaFree(d_out);
+    if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? LO_ERR_NOMEM : LO_ERR_CUDA, "value_counts_f64: %s", cudaGetErrorString(e));
+    *ndistinct = (int64_t)nd;
+    if (timing) {
+        timing->total_ms  = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        timing->h2d_bytes = (double)n * 8;
+        timing->d2h_bytes = (double)take * 16 + 8;
+        timing->launches  = ctx->launches.load() - launches0;
+    }
+    if ((int64_t)nd > capacity)
+        return fail(LO_ERR_INVALID, "%llu distinct keys do not fit the caller's capacity %lld", nd, (long long)capacity);
+    return LO_OK;
+}
+
 // text -> number for one column of cells (R-semantics "number" cast).  chars: all cells back to back;
 // offsets[i] .. offsets[i+1] delimit cell i.  values[i] = the binary64 CPython's float() returns,
 // status[i] in {0 float, 1 integer-valued, 2 empty string, 3 invalid (ValueError), 4 not decidable on device}.

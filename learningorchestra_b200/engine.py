@@ -351,3 +351,22 @@ class Engine:
         N.check(self._lib.lo_parse_number_host(self._ctx, chars.ctypes.data_as(C.c_void_p), offsets.ctypes.data_as(C.c_void_p),
                                                n, values.ctypes.data_as(C.c_void_p), status.ctypes.data_as(C.c_void_p), None))
         return values, status
+
+    def value_counts_f64_host(self, values: np.ndarray):
+        """(keys float64[g], counts uint64[g]) — exact value counts of a numeric column (GPU hash group-by),
+        -0.0 grouped with 0.0 and all NaNs together; order unspecified."""
+        values = np.ascontiguousarray(values, dtype=np.float64)
+        n = values.shape[0]
+        cap = max(min(n, 1 << 16), 1)
+        while True:
+            keys = np.empty(cap, dtype=np.float64)
+            counts = np.empty(cap, dtype=np.uint64)
+            nd = C.c_int64()
+            rc = self._lib.lo_value_counts_f64_host(self._ctx, values.ctypes.data_as(C.c_void_p), n,
+                                                    keys.ctypes.data_as(C.c_void_p), counts.ctypes.data_as(C.c_void_p),
+                                                    cap, C.byref(nd), None)
+            if rc == N.LO_ERR_INVALID and nd.value > cap:
+                cap = int(nd.value)
+                continue
+            N.check(rc)
+            return keys[:nd.value], counts[:nd.value]

@@ -5,11 +5,12 @@ Reference job (``histogram.py:25-44``): per requested field one MongoDB pipeline
 document included: it has no such field, so it lands in — and inflates — the ``null`` group), one result
 document ``{field: [{"_id": value, "count": n}, ...], "_id": k}`` per field, then ``finished: True``.
 
-Here the counting runs on the GPU.  The adapter dictionary-encodes each field's values (MongoDB's
-grouping equality, :func:`columnar.group_key`) into dense codes; fields with <= 256 distinct keys are
-packed into byte columns and counted together by ``k_hist_u8_cols`` (per-thread byte-counter
-histograms, ``lo_hist_u8_cols_host``), larger dictionaries by ``k_count_codes_u32``
-(``lo_value_counts_u32_host``).  With ``bins`` (optional extension, REST key ``bins`` / ``range``) the
+Here the counting runs on the GPU.  Number fields (every value an int / float / None) are grouped by a GPU
+hash table on the binary64 keys (``lo_value_counts_f64_host``: no host dictionary at all).  For the other
+fields (text, mixed) the adapter dictionary-encodes the values (MongoDB's grouping equality,
+:func:`columnar.group_key`) into dense codes; fields with <= 256 distinct keys are packed into byte columns
+and counted together by ``k_hist_u8_cols`` (per-thread byte-counter histograms, ``lo_hist_u8_cols_host``),
+larger dictionaries by ``k_count_codes_u32`` (``lo_value_counts_u32_host``).  With ``bins`` (optional extension, REST key ``bins`` / ``range``) the
 fields must be numeric and get the fixed-width B-semantics histogram of SURVEY.md §8c from the fused
 kernel instead.
 """
@@ -64,16 +65,30 @@ class Histogram:
 
     # ---- R-semantics: exact value counts -------------------------------------------------------------
     def __value_counts(self, documents, fields):
-        encoded = {f: columnar.dictionary_encode([d.get(f) for d in documents]) for f in fields}
         results = {}
-        small = [f for f in fields if len(encoded[f][1]) <= 256]
+        text_fields = []
+        for f in fields:
+            values = [d.get(f) for d in documents]
+            packed = columnar.numeric_column(values) if documents else None
+            if packed is None:
+                text_fields.append(f)
+                continue
+            col, valid, kind = packed                      # number field: hash group-by on the device
+            keys, counts = self.engine.value_counts_f64_host(col[valid])
+            groups = [{"_id": (int(k) if kind == "int" else float(k)), "count": int(c)} for k, c in zip(keys, counts)]
+            nulls = int((~valid).sum())                    # None / missing (the metadata document among them)
+            if nulls:
+                groups.append({"_id": None, "count": nulls})
+            results[f] = groups
+        encoded = {f: columnar.dictionary_encode([d.get(f) for d in documents]) for f in text_fields}
+        small = [f for f in text_fields if len(encoded[f][1]) <= 256]
         if small and documents:
             cols = [encoded[f][0].astype(np.uint8) for f in small]
             counts, _ = self.engine.hist_u8_cols_host(cols)
             for j, f in enumerate(small):
                 reps = encoded[f][1]
                 results[f] = [{"_id": reps[c], "count": int(counts[j][c])} for c in range(len(reps))]
-        for f in fields:
+        for f in text_fields:
             if f in results:
                 continue
             codes, reps = encoded[f]

@@ -226,3 +226,22 @@ def test_minmax_prepass(engine):
         f = bn.cast_f64_f32(table[c])
         fin = f[np.isfinite(f)]
         assert mn[c] == fin.min() and mx[c] == fin.max() and cnt[c] == fin.size
+
+
+def test_gpu_hash_group_by_on_numeric_columns(engine):
+    from collections import Counter
+    rng = np.random.default_rng(11)
+    cases = [
+        rng.integers(0, 3, 500_003).astype(np.float64),                       # 3 hot keys (warp aggregation path)
+        rng.integers(-50_000, 50_000, 700_001).astype(np.float64),           # many keys
+        np.round(rng.normal(0, 10, 300_000), 2),
+        np.array([0.0, -0.0, np.nan, float.fromhex("0x1.8p1"), np.nan, 1e300, -1e300, np.inf, -np.inf, 5e-324] * 1000),
+        np.full(200_000, 7.25),
+        np.arange(100_000, dtype=np.float64),                                 # all distinct (> initial capacity)
+    ]
+    for x in cases:
+        keys, counts = engine.value_counts_f64_host(x)
+        got = {rsem.group_key(float(k)): int(c) for k, c in zip(keys, counts)}
+        exp = Counter(rsem.group_key(float(v)) for v in x)
+        assert got == dict(exp)
+        assert int(counts.sum()) == x.size and len(keys) == len(exp)
