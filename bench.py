@@ -220,10 +220,26 @@ def run_gpu(args) -> None:
     hi = np.full(k, GEN_HI, np.float32)
     torch.cuda.synchronize()
 
-    peer = None
-    if world > 1 and args.merge == "p2p":
+    # N > 1: "p2p" fuses the merge into the kernel's flush (system-scope REDs into rank 0's matrix over NVLink);
+    # "nccl" is local counts + one all-reduce.  "auto" = p2p when the CUDA-IPC setup succeeds on every rank and a
+    # probe step completes without a flag time-out, else nccl — both are GPU paths, the line says which ran.
+    peer, merge_note = None, "nccl"
+    if world > 1 and args.merge in ("p2p", "auto"):
         from learningorchestra_b200.sharding import PeerReduce
-        peer = PeerReduce(eng, k, NBINS)
+        ok = torch.ones(1, device="cuda")
+        try:
+            peer = PeerReduce(eng, k, NBINS)
+        except Exception as exc:          # e.g. IPC not permitted in this container
+            log(f"[rank {rank}] peer-memory merge unavailable: {exc!r}")
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if float(ok[0]) == 0.0:
+            if args.merge == "p2p":
+                raise SystemExit("--merge p2p requested but the peer-memory setup failed")
+            if peer is not None:
+                peer.close()
+            peer = None
+        merge_note = "p2p" if peer is not None else "nccl (p2p setup failed)"
 
     kev = []   # (start, end) events around the fused kernel only, for the roofline
 
@@ -250,6 +266,18 @@ def run_gpu(args) -> None:
     for _ in range(args.warmup):
         step(False)
     torch.cuda.synchronize()
+    if peer is not None:
+        bad = torch.tensor([float(peer.timed_out(stream))], device="cuda")
+        dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+        if float(bad[0]) > 0:
+            if args.merge == "p2p":
+                raise SystemExit("peer-memory merge timed out during warm-up")
+            log(f"[rank {rank}] peer-memory merge timed out in warm-up; using the NCCL all-reduce")
+            peer.close()
+            peer, merge_note = None, "nccl (p2p timed out in warm-up)"
+            for _ in range(args.warmup):
+                step(False)
+            torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -339,6 +367,7 @@ def run_gpu(args) -> None:
             "config": {"workload": f"fused project+cast+{NBINS}-bin histogram, {total_rows} x {ncols} fp64 -> fp32, "
                                    f"K={k} (permutation), columnar, range [{GEN_LO}, {GEN_HI}]",
                        "rows": total_rows, "cols": ncols, "k": k, "nbins": NBINS, "rows_per_gpu": nrows,
+                       "merge": merge_note if world > 1 else None,
                        "parallelism": (f"row-range shards x{world}, " + (
                            f"one NCCL all-reduce of {k}x{NBINS} uint64 per step" if peer is None else
                            "merge fused into the kernel flush: system-scope RED.64 into rank 0's matrix over NVLink (CUDA IPC)"))
@@ -380,7 +409,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--merge", default="nccl", choices=["nccl", "p2p"],
+    ap.add_argument("--merge", default="auto", choices=["auto", "nccl", "p2p"],
                     help="N > 1: how partial histograms are merged (NCCL all-reduce, or fused peer-memory REDs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
