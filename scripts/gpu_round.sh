@@ -16,3 +16,8 @@ if [[ "$*" != *noncu* ]]; then
       -o gpurun_out/prof_$TAG -f python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu > gpurun_out/ncu_full_$TAG.log 2>&1
   tail -3 gpurun_out/ncu_full_$TAG.log
 fi
+if [[ "$*" == *u8ncu* ]]; then
+  timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_hist_u8_cols -s 4 -c 1 \
+      -o gpurun_out/prof_u8_$TAG -f python scripts/kbench.py 1000000 8 > gpurun_out/ncu_u8_$TAG.log 2>&1
+  tail -2 gpurun_out/ncu_u8_$TAG.log
+fi

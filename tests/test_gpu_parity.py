@@ -231,3 +231,47 @@ def test_unsafe_divisors_take_the_ieee_kernel(engine):
         _, exp = bn.project_cast_hist(x[None, :], [0], nbins, [lo], [hi])
         np.testing.assert_array_equal(got, exp)
         t.free()
+
+
+def test_empty_inputs(engine):
+    t = engine.table("f64", 0, 3)
+    out = engine.table("f32", 0, 3)
+    c = engine.project_cast_hist(t, [0, 1, 2], 16, -1.0, 1.0, out=out).to_numpy()
+    assert c.sum() == 0
+    counts, timing = engine.project_cast_hist_host([np.empty(0), np.empty(0)], 8, -1.0, 1.0, out=[np.empty(0, np.float32)] * 2)
+    assert counts.shape == (2, 8) and counts.sum() == 0 and timing["launches"] == 0
+    c8, _ = engine.hist_u8_cols_host([np.empty(0, np.uint8)])
+    assert c8.sum() == 0
+    vals, st = engine.parse_number_host([])
+    assert vals.shape == (0,) and st.shape == (0,)
+    k, n = engine.value_counts_f64_host(np.empty(0))
+    assert k.size == 0 and n.size == 0
+    t.free(); out.free()
+
+
+def test_concurrent_callers_share_one_engine(engine):
+    """The C ABI is documented re-entrant: four Python threads (ctypes drops the GIL) hammer one context."""
+    import threading
+    errors = []
+
+    def work(seed):
+        try:
+            table = bn.synth_table_f64(1, SEED + seed, 3, seed * 1000, 150_000 + seed)
+            _, exp = bn.project_cast_hist(table, [2, 0], 64, [-1000.0] * 2, [1000.0] * 2)
+            for _ in range(5):
+                t = engine.table_from_numpy(table)
+                got = engine.project_cast_hist(t, [2, 0], 64, -1000.0, 1000.0).to_numpy()
+                np.testing.assert_array_equal(got, exp)
+                t.free()
+                cols = [np.ascontiguousarray(table[2]), np.ascontiguousarray(table[0])]
+                got_h, _ = engine.project_cast_hist_host(cols, 64, -1000.0, 1000.0)
+                np.testing.assert_array_equal(got_h, exp)
+        except Exception as exc:      # noqa: BLE001
+            errors.append(exc)
+
+    threads = [threading.Thread(target=work, args=(s,)) for s in range(4)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
