@@ -39,28 +39,30 @@ class DataType:
         self.last_job = None
 
     def field_converter(self, filename, field, field_type):
-        documents = columnar.data_rows(self.database_connector.find(filename, {}))
-        updates = {}
+        rows = columnar.data_rows(self.database_connector.find(filename, {}))
         failure = None
         if field_type == self.FLOAT32_TYPE:
-            updates = self.__gpu_float32(documents, field)
+            changes = self.__gpu_float32(rows, field)
         elif field_type == self.NUMBER_TYPE:
-            updates, failure = self.__gpu_number(documents, field)
+            changes, failure = self.__gpu_number(rows, field)
+        elif field_type == self.STRING_TYPE:
+            changes = self.__to_text(rows, field)
         else:
-            for document in documents:
-                values = {}
-                if field_type == self.STRING_TYPE:
-                    if document[field] == str:
-                        continue
-                    if document[field] is None:
-                        values[field] = ""
-                    else:
-                        values[field] = str(document[field])
-                if values:
-                    updates[document[self.DOCUMENT_ID_NAME]] = values
-        self.database_connector.update_by_id(filename, updates)
+            changes = {}                      # unknown type: the reference issues an empty $set
+        self.database_connector.update_by_id(filename, changes)
         if failure is not None:
             raise failure
+
+    def __to_text(self, rows, field):
+        """``data_type_update.py:22-28``: ``None -> ""``, anything else ``str(v)``; the reference's guard
+        ``document[field] == str`` compares a value with the type object and is never true."""
+        changes = {}
+        for row in rows:
+            cell = row[field]
+            if cell == str:
+                continue
+            changes[row[self.DOCUMENT_ID_NAME]] = {field: "" if cell is None else str(cell)}
+        return changes
 
     def __gpu_number(self, documents, field):
         """``data_type_update.py:30-43`` with the ``float(str)`` of every text cell done by the GPU parser."""
