@@ -150,6 +150,11 @@ int lo_project_cast_hist_dev(lo_ctx *ctx, const lo_table *in, const int32_t *col
 /* per-column 256-bin value counts of LO_U8 columns; counts_dev: uint64[k*256], accumulated */
 int lo_hist_u8_cols_dev(lo_ctx *ctx, const lo_table *in, const int32_t *col_idx, int32_t k,
                         uint64_t *counts_dev, void *stream);
+/* range pre-pass on RESIDENT columns: out_dev = device uint64[3*k] (lo_counts_alloc), zeroed by the call;
+ * download it (lo_counts_download) and decode with lo_minmax_decode (host-only helper). */
+int lo_minmax_cast_dev(lo_ctx *ctx, const lo_table *in, const int32_t *col_idx, int32_t k,
+                       uint64_t *out_dev, void *stream);
+int lo_minmax_decode(const uint64_t *raw, int32_t k, float *mins, float *maxs, uint64_t *nfinite);
 /* device scratch for counts */
 int lo_counts_alloc(lo_ctx *ctx, int64_t n, uint64_t **out_dev);
 int lo_counts_free(lo_ctx *ctx, uint64_t *counts_dev);

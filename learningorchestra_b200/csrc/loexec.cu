@@ -702,6 +702,39 @@ int lo_dev_read_u64(lo_ctx *ctx, const uint64_t *dev_ptr, int64_t n, uint64_t *h
     return LO_OK;
 }
 
+// per-column min / max / count of the finite cast values of RESIDENT columns; out_dev: uint64[3*k], zeroed here.
+// Decode on the host with lo_minmax_decode.
+int lo_minmax_cast_dev(lo_ctx *ctx, const lo_table *in, const int32_t *col_idx, int32_t k, uint64_t *out_dev, void *stream) {
+    LO_TRY(check_ctx(ctx));
+    if (!in || in->dtype != LO_F64) return fail(LO_ERR_INVALID, "input table must be LO_F64");
+    LO_TRY(check_cols(in, col_idx, k));
+    if (!out_dev) return fail(LO_ERR_INVALID, "out_dev is NULL");
+    cudaStream_t s = pick(ctx, stream);
+    LO_CUDA(cudaMemsetAsync(out_dev, 0, (size_t)k * 24, s));
+    if (in->nrows == 0) return LO_OK;
+    for (int j = 0; j < k; ++j) {
+        dim3 grid((unsigned)std::min<int64_t>((in->nrows + 2047) / 2048, ctx->sm_count * 4), 1);
+        lo::k_minmax_cast<<<grid, 256, 0, s>>>(in->base + (int64_t)col_idx[j] * in->pitch, in->pitch, in->nrows,
+                                               (unsigned long long *)out_dev + 3 * j);
+        LO_CUDA(cudaGetLastError());
+        ctx->launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    return LO_OK;
+}
+
+// raw[3*k] (as downloaded from lo_minmax_cast_dev) -> mins / maxs / nfinite
+int lo_minmax_decode(const uint64_t *raw, int32_t k, float *mins, float *maxs, uint64_t *nfinite) {
+    if (!raw || !mins || !maxs || !nfinite || k < 0) return fail(LO_ERR_INVALID, "bad arguments");
+    for (int j = 0; j < k; ++j) {
+        nfinite[j] = raw[(size_t)j * 3 + 2];
+        uint32_t omin = ~(uint32_t)raw[(size_t)j * 3 + 0], omax = (uint32_t)raw[(size_t)j * 3 + 1];
+        auto unorder = [](uint32_t o) { uint32_t b = (o & 0x80000000u) ? (o ^ 0x80000000u) : ~o; float f; memcpy(&f, &b, 4); return f; };
+        mins[j] = nfinite[j] ? unorder(omin) : 0.f;
+        maxs[j] = nfinite[j] ? unorder(omax) : 0.f;
+    }
+    return LO_OK;
+}
+
 // ---- hot path, device resident ------------------------------------------------------------------
 int lo_project_cast_dev(lo_ctx *ctx, const lo_table *in, const int32_t *col_idx, int32_t k, lo_table *out,
                         void *stream) {

@@ -123,6 +123,8 @@ class Engine:
 
     # ---- lifetime ---------------------------------------------------------------------------------
     def close(self) -> None:
+        if self._ctx is not None and getattr(self, "_resident", None) is not None:
+            self._resident.clear()
         if self._ctx is not None:
             for p in list(self._pinned.values()):
                 self._lib.lo_host_free(self._ctx, p)
@@ -370,3 +372,23 @@ class Engine:
                 continue
             N.check(rc)
             return keys[:nd.value], counts[:nd.value]
+
+    def minmax_cast(self, table: DeviceTable, col_idx, stream=None):
+        """(min, max, n_finite) of the fp32-cast values of resident columns (range pre-pass on the device)."""
+        idx, k = _i32(col_idx)
+        raw = self.counts(k, 3)
+        N.check(self._lib.lo_minmax_cast_dev(self._ctx, table._h, idx, k, raw._ptr, _stream_ptr(stream)))
+        host = raw.to_numpy(stream)
+        raw.free()
+        mins, maxs, cnt = np.zeros(k, np.float32), np.zeros(k, np.float32), np.zeros(k, np.uint64)
+        N.check(self._lib.lo_minmax_decode(host.ctypes.data_as(C.c_void_p), k, mins.ctypes.data_as(C.c_void_p),
+                                           maxs.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.c_void_p)))
+        return mins, maxs, cnt
+
+    @property
+    def resident(self):
+        """Numeric columns of datasets kept in HBM between requests (:mod:`table_cache`)."""
+        if getattr(self, "_resident", None) is None:
+            from .table_cache import ResidentTables
+            self._resident = ResidentTables(self)
+        return self._resident

@@ -48,10 +48,10 @@ class Histogram:
         try:
             if self.engine is None:
                 raise RuntimeError("Histogram needs an Engine: the counting has no CPU fallback")
-            documents = self.database_connector.find(parent_filename, {})      # unfiltered, like $group
             if bins:
-                results = self.__binned(documents, fields, int(bins), value_range)
+                results = self.__binned(parent_filename, fields, int(bins), value_range)
             else:
+                documents = self.database_connector.find(parent_filename, {})  # unfiltered, like $group
                 results = self.__value_counts(documents, fields)
             document_id = 1
             for field in fields:
@@ -97,19 +97,18 @@ class Histogram:
         return results
 
     # ---- B-semantics: fixed-width bins of the fp32-cast value -----------------------------------------
-    def __binned(self, documents, fields, bins, value_range):
-        rows = columnar.data_rows(documents)
-        cols = []
-        for f in fields:
-            packed = columnar.numeric_column([d.get(f) for d in rows])
-            if packed is None:
-                raise ValueError(f"field {f!r} is not numeric; run /fieldTypes first")
-            cols.append(packed[0])          # nulls are NaN: skipped by the kernel
+    def __binned(self, parent_filename, fields, bins, value_range):
+        """Columns come from the GPU-resident copy of the dataset (built from the documents on first use,
+        reused until the collection is written to): no document scan, no H2D on a repeat request."""
+        data = self.engine.resident.ensure(self.database_connector, parent_filename, fields)
+        cols = [data.column[f] for f in fields]            # nulls are NaN in the slabs: skipped by the kernel
         if value_range is None:
-            lo, hi, _cnt = self.engine.minmax_cast_host(cols)
+            lo, hi, _cnt = self.engine.minmax_cast(data.table, cols)
         else:
             lo = np.full(len(fields), value_range[0], np.float32)
             hi = np.full(len(fields), value_range[1], np.float32)
-        counts, _ = self.engine.project_cast_hist_host(cols, bins, lo, hi)
+        dev_counts = self.engine.project_cast_hist(data.table, cols, bins, lo, hi)
+        counts = dev_counts.to_numpy()
+        dev_counts.free()
         return {f: {"bins": bins, "range": [float(lo[j]), float(hi[j])], "counts": [int(c) for c in counts[j]]}
                 for j, f in enumerate(fields)}

@@ -1,0 +1,91 @@
+"""Datasets resident in HBM between requests.
+
+In the reference every request re-reads the whole Mongo collection (Spark ``load`` in
+``projection_image/projection.py:35-37``, one ``$group`` scan per field in
+``histogram_image/histogram.py:31-36``).  Here the numeric columns of a dataset are packed once into a
+columnar :class:`~learningorchestra_b200.engine.DeviceTable` and stay on the GPU: later histogram /
+projection requests on the same dataset run on the resident slabs (``lo_project_cast_hist_dev``) with no
+document scan and no host->device copy, which is the regime ``bench.py``'s ``value`` measures.
+
+Staleness: the in-process :class:`~learningorchestra_b200.utils.Database` bumps ``version(filename)`` on every
+write to data rows; a cached table is used only while its version matches.  A ``Database`` without
+``version`` (foreign object) is never cached.  Eviction: least recently used beyond ``max_bytes``.
+"""
+from __future__ import annotations
+
+import threading
+from collections import OrderedDict
+
+import numpy as np
+
+from . import columnar
+
+
+class ResidentDataset:
+    def __init__(self, version, ids, fields, kinds, nulls, table):
+        self.version, self.ids, self.fields, self.kinds, self.nulls, self.table = version, ids, fields, kinds, nulls, table
+        self.column = {f: i for i, f in enumerate(fields)}
+
+    @property
+    def nbytes(self) -> int:
+        return self.table.pitch_bytes * self.table.ncols
+
+
+class ResidentTables:
+    def __init__(self, engine, max_bytes: int = 64 << 30):
+        self.engine, self.max_bytes = engine, max_bytes
+        self._entries: "OrderedDict[str, ResidentDataset]" = OrderedDict()
+        self._lock = threading.RLock()
+        self.hits = self.misses = 0
+
+    def ensure(self, database, filename: str, fields) -> ResidentDataset:
+        """Resident table holding (at least) ``fields`` of ``filename``; built from the documents on a miss.
+        Raises ValueError if a requested field is not numeric."""
+        version = database.version(filename) if hasattr(database, "version") else None
+        with self._lock:
+            entry = self._entries.get(filename)
+            if entry is not None and version is not None and entry.version == version and all(f in entry.column for f in fields):
+                self._entries.move_to_end(filename)
+                self.hits += 1
+                return entry
+            self.misses += 1
+            keep = [f for f in (entry.fields if entry is not None and entry.version == version else []) if f not in fields]
+            wanted = list(fields) + keep
+            rows = columnar.data_rows(database.find(filename, {}))
+            rows.sort(key=lambda d: d["_id"])
+            cols, kinds, nulls, names = [], [], [], []
+            for f in wanted:
+                packed = columnar.numeric_column([d.get(f) for d in rows])
+                if packed is None:
+                    if f in fields:
+                        raise ValueError(f"field {f!r} is not numeric; run /fieldTypes first")
+                    continue                 # a previously resident column that stopped being numeric: drop it
+                names.append(f); cols.append(packed[0]); kinds.append(packed[2]); nulls.append(int((~packed[1]).sum()))
+            table = self.engine.table_from_numpy(cols) if rows else self.engine.table("f64", 0, max(len(cols), 1))
+            new = ResidentDataset(version, np.array([d["_id"] for d in rows], dtype=np.int64), names, kinds, nulls, table)
+            if entry is not None:
+                entry.table.free()
+            if version is not None:
+                self._entries[filename] = new
+                self._entries.move_to_end(filename)
+                self._evict()
+            return new
+
+    def _evict(self):
+        total = sum(e.nbytes for e in self._entries.values())
+        while total > self.max_bytes and len(self._entries) > 1:
+            _name, old = self._entries.popitem(last=False)
+            total -= old.nbytes
+            old.table.free()
+
+    def invalidate(self, filename: str) -> None:
+        with self._lock:
+            entry = self._entries.pop(filename, None)
+            if entry is not None:
+                entry.table.free()
+
+    def clear(self) -> None:
+        with self._lock:
+            for e in self._entries.values():
+                e.table.free()
+            self._entries.clear()

@@ -46,7 +46,17 @@ class Database:
     def __init__(self, database_url=None, replica_set=None, database_port=None, database_name="database"):
         self.database_name = database_name
         self._collections: "OrderedDict[str, list[dict]]" = OrderedDict()
+        self._versions: dict = {}
         self._lock = threading.RLock()
+
+    def version(self, filename) -> int:
+        """Bumped on every write that touches DATA rows of the collection (lets the GPU-resident column cache
+        know when its copy is stale; flipping flags in the metadata document does not count)."""
+        with self._lock:
+            return self._versions.get(filename, 0)
+
+    def _touch(self, filename):
+        self._versions[filename] = self._versions.get(filename, 0) + 1
 
     # -- reads ---------------------------------------------------------------------------------------
     def get_filenames(self):
@@ -73,16 +83,21 @@ class Database:
     def insert_one_in_file(self, filename, json_object):
         with self._lock:
             self._collections.setdefault(filename, []).append(dict(json_object))
+            if json_object.get(DOCUMENT_ID_NAME) != METADATA_DOCUMENT_ID:
+                self._touch(filename)
 
     def insert_many_in_file(self, filename, json_objects):
         with self._lock:
             self._collections.setdefault(filename, []).extend(dict(o) for o in json_objects)
+            self._touch(filename)
 
     def update_one(self, filename, new_value, query):
         with self._lock:
             for d in self._collections.get(filename, []):
                 if _matches(d, query):
                     d.update(new_value)
+                    if d.get(DOCUMENT_ID_NAME) != METADATA_DOCUMENT_ID:
+                        self._touch(filename)
                     return
 
     def update_by_id(self, filename, updates: dict):
@@ -93,10 +108,13 @@ class Database:
                 u = updates.get(d.get(DOCUMENT_ID_NAME))
                 if u:
                     d.update(u)
+            if updates:
+                self._touch(filename)
 
     def delete_file(self, filename):
         with self._lock:
             self._collections.pop(filename, None)
+            self._touch(filename)
 
     @staticmethod
     def collection_database_url(database_url, database_name, database_filename, database_replica_set):

@@ -245,3 +245,44 @@ def test_gpu_hash_group_by_on_numeric_columns(engine):
         exp = Counter(rsem.group_key(float(v)) for v in x)
         assert got == dict(exp)
         assert int(counts.sum()) == x.size and len(keys) == len(exp)
+
+
+def test_resident_dataset_cache(engine):
+    """Binned histograms run on the HBM-resident copy of the dataset: second request = cache hit, same counts;
+    a write to the collection invalidates it."""
+    engine.resident.clear()
+    db = _titanic_db()
+    job = DataType(db, utils.DataTypeMetadata(db), engine)
+    job.convert_existent_file("titanic", {"Age": "number", "Fare": "number", "Pclass": "number"})
+    job.wait()
+    rows = sorted((d for d in db.find("titanic", {}) if d["_id"] != 0), key=lambda d: d["_id"])
+
+    def expect(field, nb, lo, hi):
+        vals = np.array([np.nan if r[field] is None else float(r[field]) for r in rows])
+        return bn.hist_f32(bn.cast_f64_f32(vals), lo, hi, nb).tolist()
+
+    h0, m0 = engine.resident.hits, engine.resident.misses
+    for n, (fields, out) in enumerate([(["Age", "Fare"], "r1"), (["Fare"], "r2"), (["Age"], "r3")]):
+        h = Histogram(db, utils.HistogramMetadata(db), engine)
+        h.create_file("titanic", out, list(fields), bins=16, value_range=[0, 128])
+        h.wait()
+        docs = sorted((d for d in db.find(out, {}) if d["_id"] != 0), key=lambda d: d["_id"])
+        for d, f in zip(docs, fields):
+            assert d[f]["counts"] == expect(f, 16, 0, 128)
+    assert engine.resident.misses == m0 + 1 and engine.resident.hits == h0 + 2
+    # a field that was not resident yet extends the table (miss), keeping the old columns
+    h = Histogram(db, utils.HistogramMetadata(db), engine)
+    h.create_file("titanic", "r4", ["Pclass"], bins=3)             # range from the device min/max pre-pass
+    h.wait()
+    d = [x for x in db.find("r4", {}) if x["_id"] == 1][0]
+    assert d["Pclass"]["range"] == [1.0, 3.0] and d["Pclass"]["counts"] == expect("Pclass", 3, 1.0, 3.0)
+    assert engine.resident.misses == m0 + 2
+    # write -> stale -> rebuilt, and the new values are what gets counted
+    db.update_one("titanic", {"Age": 127.0}, {"_id": 1})
+    rows[0]["Age"] = 127.0
+    h = Histogram(db, utils.HistogramMetadata(db), engine)
+    h.create_file("titanic", "r5", ["Age"], bins=16, value_range=[0, 128])
+    h.wait()
+    d = [x for x in db.find("r5", {}) if x["_id"] == 1][0]
+    assert d["Age"]["counts"] == expect("Age", 16, 0, 128) and engine.resident.misses == m0 + 3
+    engine.resident.clear()
