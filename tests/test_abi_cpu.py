@@ -64,3 +64,24 @@ def test_package_never_imports_the_oracle():
             assert "oracle" not in text.lower() or all(
                 "import" not in line and "dlopen" not in line and "CDLL" not in line
                 for line in text.splitlines() if "oracle" in line.lower()), path
+
+
+def _build_c_consumer():
+    from learningorchestra_b200 import _native
+    exe = ROOT / "tests" / "native" / "_build" / "abi_smoke"
+    exe.parent.mkdir(exist_ok=True)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-O1", "-I", str(ROOT / "include"),
+                    str(ROOT / "tests" / "native" / "abi_smoke.c"), "-o", str(exe),
+                    "-L", str(_native.LIB_PATH.parent), "-lloexec", f"-Wl,-rpath,{_native.LIB_PATH.parent}"], check=True)
+    return exe
+
+
+def test_plain_c_program_links_against_the_abi(built):
+    """include/loexec.h is plain C99 and the .so links without any C++ / CUDA / torch on the consumer side."""
+    import torch
+    exe = _build_c_consumer()
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    if torch.cuda.is_available():
+        assert out.returncode == 0, out.stderr
+    else:
+        assert out.returncode == 3 and "no CUDA device" in out.stderr      # loud, documented failure

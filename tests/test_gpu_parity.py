@@ -275,3 +275,10 @@ def test_concurrent_callers_share_one_engine(engine):
     for th in threads:
         th.join()
     assert not errors, errors
+
+
+def test_plain_c_consumer_runs_the_hot_path(engine):
+    import subprocess
+    from test_abi_cpu import _build_c_consumer
+    out = subprocess.run([str(_build_c_consumer())], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "abi_smoke ok" in out.stdout, out.stderr
