@@ -220,6 +220,13 @@ int lo_value_counts_f64_host(lo_ctx *ctx, const double *values, int64_t n, doubl
                              uint64_t *counts_out, int64_t capacity, int64_t *ndistinct,
                              lo_host_timing *timing);
 
+/* The same for one TEXT column: cell i = chars[offsets[i] .. offsets[i+1]) (offsets[0] == 0, n < 2^31).  Keys are
+ * compared byte for byte on the device (exact whatever the hash does).  rep_rows_out[g] = row index of one member
+ * of group g — the caller reads the key from its own cell — and counts_out[g] its size; order unspecified. */
+int lo_value_counts_str_host(lo_ctx *ctx, const uint8_t *chars, const int64_t *offsets, int64_t n,
+                             int64_t *rep_rows_out, uint64_t *counts_out, int64_t capacity,
+                             int64_t *ndistinct, lo_host_timing *timing);
+
 /* Text -> number for one column of cells: the reference's REAL cast, `float(document[field])` followed by
  * `is_integer()` (data_type_handler_image/data_type_update.py:40-43), for every cell at once on the GPU.
  * chars holds all cells back to back, cell i = chars[offsets[i] .. offsets[i+1]).  values[i] receives exactly

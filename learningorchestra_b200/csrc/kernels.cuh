@@ -684,6 +684,74 @@ __global__ void k_hash_compact(const unsigned long long *__restrict__ keys, cons
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// exact value counts of a TEXT column (cells packed as chars + offsets): GPU hash group-by on the bytes.
+// A slot holds (33 bits of the cell's hash | 31-bit row index of the group's representative); a probing
+// thread whose hash bits match compares its bytes with the representative's (the input is immutable), so the
+// result is exact whatever the hash does.  Lanes of a warp with the same 64-bit hash are merged first
+// (match.any), after verifying byte equality with the group leader.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long hash_bytes(const uint8_t *p, long long len) {
+    unsigned long long h = 0xCBF29CE484222325ull ^ (unsigned long long)len;
+    for (long long i = 0; i < len; ++i) h = (h ^ p[i]) * 0x100000001B3ull;     // FNV-1a
+    return splitmix64(h);
+}
+
+__device__ __forceinline__ bool same_cell(const uint8_t *chars, const long long *offsets, long long a, long long b) {
+    const long long a0 = offsets[a], b0 = offsets[b], la = offsets[a + 1] - a0;
+    if (la != offsets[b + 1] - b0) return false;
+    for (long long i = 0; i < la; ++i)
+        if (chars[a0 + i] != chars[b0 + i]) return false;
+    return true;
+}
+
+__global__ void k_hash_count_str(const uint8_t *__restrict__ chars, const long long *__restrict__ offsets, long long n,
+                                 unsigned long long *__restrict__ slots, unsigned long long *__restrict__ counts,
+                                 unsigned long long mask) {
+    for (long long i0 = blockIdx.x * (long long)blockDim.x; i0 < n; i0 += (long long)gridDim.x * blockDim.x) {
+        const long long i = i0 + threadIdx.x;
+        const bool live = i < n;
+        const unsigned active = __ballot_sync(0xffffffffu, live);
+        if (!live) continue;
+        const unsigned long long h = hash_bytes(chars + offsets[i], offsets[i + 1] - offsets[i]);
+        const unsigned peers = __match_any_sync(active, h);
+        const int leader = __ffs(peers) - 1;
+        const long long leader_row = __shfl_sync(active, i, leader);
+        const bool same = ((int)(threadIdx.x & 31) == leader) || same_cell(chars, offsets, i, leader_row);
+        const unsigned eq = __ballot_sync(active, same);
+        unsigned long long add;
+        if ((int)(threadIdx.x & 31) == leader) add = (unsigned long long)__popc(peers & eq);
+        else if (!same) add = 1ull;               // hash collision inside the warp: insert on its own
+        else continue;                            // counted by the leader
+        const unsigned long long tag = (h >> 31) << 31;                     // top 33 bits
+        const unsigned long long mine = tag | (unsigned long long)i;        // i < 2^31
+        unsigned long long s = splitmix64(h) & mask;
+        for (;;) {
+            unsigned long long cur = atomicCAS(slots + s, kEmptyKey, mine);
+            if (cur == kEmptyKey) { atomicAdd(counts + s, add); break; }
+            if ((cur >> 31) == (tag >> 31) && same_cell(chars, offsets, i, (long long)(cur & 0x7FFFFFFFull))) {
+                atomicAdd(counts + s, add);
+                break;
+            }
+            s = (s + 1) & mask;
+        }
+    }
+}
+
+__global__ void k_hash_compact_str(const unsigned long long *__restrict__ slots, const unsigned long long *__restrict__ counts,
+                                   unsigned long long nslots, long long *__restrict__ out_rows,
+                                   unsigned long long *__restrict__ out_counts, unsigned long long capacity,
+                                   unsigned long long *__restrict__ n_out) {
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < nslots;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long k = slots[i];
+        if (k != kEmptyKey) {
+            const unsigned long long pos = atomicAdd(n_out, 1ull);
+            if (pos < capacity) { out_rows[pos] = (long long)(k & 0x7FFFFFFFull); out_counts[pos] = counts[i]; }
+        }
+    }
+}
+
 // R-semantics cast "number" (data_type_update.py:40-43): one cell per thread, CPython float() grammar,
 // correctly rounded binary64 (parse_number.cuh) + the is_integer() flag the adapter turns into int(v)
 __global__ void k_parse_number(const uint8_t *__restrict__ chars, const long long *__restrict__ offsets, long long n,

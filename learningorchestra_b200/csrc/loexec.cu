@@ -981,6 +981,68 @@ int lo_value_counts_f64_host(lo_ctx *ctx, const double *values, int64_t n, doubl
     return LO_OK;
 }
 
+// exact value counts of one TEXT column (cells = chars[offsets[i] .. offsets[i+1])): GPU hash group-by on the bytes.
+// rep_rows_out[g] = row index of one member of group g (the caller reads the key from its own cell), counts_out[g].
+int lo_value_counts_str_host(lo_ctx *ctx, const uint8_t *chars, const int64_t *offsets, int64_t n, int64_t *rep_rows_out,
+                             uint64_t *counts_out, int64_t capacity, int64_t *ndistinct, lo_host_timing *timing) {
+    LO_TRY(check_ctx(ctx));
+    if (n < 0 || capacity < 0) return fail(LO_ERR_INVALID, "negative size");
+    if (n > 0x7fffffffll) return fail(LO_ERR_INVALID, "at most 2^31-1 rows per call");
+    if (!ndistinct) return fail(LO_ERR_INVALID, "ndistinct is NULL");
+    *ndistinct = 0;
+    if (n == 0) return LO_OK;
+    if (!offsets || (capacity > 0 && (!rep_rows_out || !counts_out))) return fail(LO_ERR_INVALID, "NULL argument");
+    const int64_t nbytes = offsets[n] - offsets[0];
+    if (offsets[0] != 0 || nbytes < 0 || (nbytes > 0 && !chars)) return fail(LO_ERR_INVALID, "offsets must start at 0 and be non-decreasing");
+    for (int64_t i = 0; i < n; ++i)
+        if (offsets[i + 1] < offsets[i]) return fail(LO_ERR_INVALID, "offsets must be non-decreasing (row %lld)", (long long)i);
+    const auto t0 = std::chrono::steady_clock::now();
+    const int64_t launches0 = ctx->launches.load();
+    unsigned long long nslots = 1024;
+    while (nslots < 2ull * (unsigned long long)n) nslots <<= 1;
+    const size_t out_n = (size_t)std::max<int64_t>(capacity, 1);
+    uint8_t *d_chars = nullptr;
+    long long *d_off = nullptr;
+    unsigned long long *d_slots = nullptr, *d_counts = nullptr, *d_out = nullptr;
+    cudaStream_t s = ctx->stream;
+    cudaError_t e = cudaMalloc((void **)&d_chars, (size_t)std::max<int64_t>(nbytes, 1));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_off, (size_t)(n + 1) * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_slots, nslots * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_counts, nslots * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_out, (2 * out_n + 1) * 8);
+    if (e == cudaSuccess && nbytes) e = cudaMemcpyAsync(d_chars, chars, (size_t)nbytes, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_off, offsets, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_slots, 0xFF, nslots * 8, s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_counts, 0, nslots * 8, s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_out + 2 * out_n, 0, 8, s);
+    if (e == cudaSuccess) {
+        const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 8);
+        lo::k_hash_count_str<<<grid, 256, 0, s>>>(d_chars, d_off, n, d_slots, d_counts, nslots - 1);
+        lo::k_hash_compact_str<<<ctx->sm_count * 8, 256, 0, s>>>(d_slots, d_counts, nslots, (long long *)d_out, d_out + out_n,
+                                                                  (unsigned long long)capacity, d_out + 2 * out_n);
+        e = cudaGetLastError();
+        ctx->launches.fetch_add(2, std::memory_order_relaxed);
+    }
+    unsigned long long nd = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&nd, d_out + 2 * out_n, 8, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    const size_t take = (size_t)std::min<unsigned long long>(nd, (unsigned long long)capacity);
+    if (e == cudaSuccess && take) e = cudaMemcpy(rep_rows_out, d_out, take * 8, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && take) e = cudaMemcpy(counts_out, d_out + out_n, take * 8, cudaMemcpyDeviceToHost);
+    cudaFree(d_chars); cudaFree(d_off); cudaFree(d_slots); cudaFree(d_counts); cudaFree(d_out);
+    if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? LO_ERR_NOMEM : LO_ERR_CUDA, "value_counts_str: %s", cudaGetErrorString(e));
+    *ndistinct = (int64_t)nd;
+    if (timing) {
+        timing->total_ms  = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        timing->h2d_bytes = (double)nbytes + (double)(n + 1) * 8;
+        timing->d2h_bytes = (double)take * 16 + 8;
+        timing->launches  = ctx->launches.load() - launches0;
+    }
+    if ((int64_t)nd > capacity)
+        return fail(LO_ERR_INVALID, "%llu distinct keys do not fit the caller's capacity %lld", nd, (long long)capacity);
+    return LO_OK;
+}
+
 // text -> number for one column of cells (R-semantics "number" cast).  chars: all cells back to back;
 // offsets[i] .. offsets[i+1] delimit cell i.  values[i] = the binary64 CPython's float() returns,
 // status[i] in {0 float, 1 integer-valued, 2 empty string, 3 invalid (ValueError), 4 not decidable on device}.

@@ -392,3 +392,26 @@ class Engine:
             from .table_cache import ResidentTables
             self._resident = ResidentTables(self)
         return self._resident
+
+    def value_counts_str_host(self, cells):
+        """cells: list of ``str`` / ``bytes``.  Returns (rep_rows int64[g], counts uint64[g]): one representative row
+        per distinct cell and the group sizes (GPU hash group-by on the bytes, exact)."""
+        enc = [c.encode("utf-8") if isinstance(c, str) else bytes(c) for c in cells]
+        n = len(enc)
+        offsets = np.zeros(n + 1, dtype=np.int64)
+        if n:
+            np.cumsum([len(b) for b in enc], out=offsets[1:])
+        chars = np.frombuffer(b"".join(enc) + b"\0", dtype=np.uint8)
+        cap = max(min(n, 1 << 16), 1)
+        while True:
+            rows = np.empty(cap, dtype=np.int64)
+            counts = np.empty(cap, dtype=np.uint64)
+            nd = C.c_int64()
+            rc = self._lib.lo_value_counts_str_host(self._ctx, chars.ctypes.data_as(C.c_void_p), offsets.ctypes.data_as(C.c_void_p),
+                                                    n, rows.ctypes.data_as(C.c_void_p), counts.ctypes.data_as(C.c_void_p),
+                                                    cap, C.byref(nd), None)
+            if rc == N.LO_ERR_INVALID and nd.value > cap:
+                cap = int(nd.value)
+                continue
+            N.check(rc)
+            return rows[:nd.value], counts[:nd.value]

@@ -6,8 +6,9 @@ document included: it has no such field, so it lands in — and inflates — the
 document ``{field: [{"_id": value, "count": n}, ...], "_id": k}`` per field, then ``finished: True``.
 
 Here the counting runs on the GPU.  Number fields (every value an int / float / None) are grouped by a GPU
-hash table on the binary64 keys (``lo_value_counts_f64_host``: no host dictionary at all).  For the other
-fields (text, mixed) the adapter dictionary-encodes the values (MongoDB's grouping equality,
+hash table on the binary64 keys (``lo_value_counts_f64_host``), text fields (every value a ``str`` / None) by a
+GPU hash table on the cells' bytes (``lo_value_counts_str_host``) — no host dictionary in either case.  For
+the remaining (mixed-type) fields the adapter dictionary-encodes the values (MongoDB's grouping equality,
 :func:`columnar.group_key`) into dense codes; fields with <= 256 distinct keys are packed into byte columns
 and counted together by ``k_hist_u8_cols`` (per-thread byte-counter histograms, ``lo_hist_u8_cols_host``),
 larger dictionaries by ``k_count_codes_u32`` (``lo_value_counts_u32_host``).  With ``bins`` (optional extension, REST key ``bins`` / ``range``) the
@@ -70,6 +71,14 @@ class Histogram:
         for f in fields:
             values = [d.get(f) for d in documents]
             packed = columnar.numeric_column(values) if documents else None
+            if packed is None and documents and all(v is None or isinstance(v, str) for v in values):
+                cells = [v for v in values if v is not None]           # text field: hash group-by on the bytes
+                rep, counts = self.engine.value_counts_str_host(cells)
+                groups = [{"_id": cells[int(r)], "count": int(c)} for r, c in zip(rep, counts)]
+                if len(cells) != len(values):
+                    groups.append({"_id": None, "count": len(values) - len(cells)})
+                results[f] = groups
+                continue
             if packed is None:
                 text_fields.append(f)
                 continue

@@ -286,3 +286,32 @@ def test_resident_dataset_cache(engine):
     d = [x for x in db.find("r5", {}) if x["_id"] == 1][0]
     assert d["Age"]["counts"] == expect("Age", 16, 0, 128) and engine.resident.misses == m0 + 3
     engine.resident.clear()
+
+
+def test_gpu_hash_group_by_on_text_columns(engine):
+    from collections import Counter
+    import random
+    rng = random.Random(5)
+    words = ["", " ", "a", "b", "ab", "ba", "male", "female", "S", "C", "Q", "é", "日本", "x" * 300] + [f"T{i}" for i in range(5000)]
+    cases = [
+        [rng.choice(words[:6]) for _ in range(200_003)],                      # few hot keys (warp aggregation)
+        [rng.choice(words) for _ in range(300_001)],                          # thousands of keys, long and non-ASCII cells
+        [f"Name{i}, Mr. Given{i % 977}" for i in range(150_000)],             # all distinct (> initial capacity)
+        ["same"] * 100_000,
+        [""] * 1000,
+    ]
+    for cells in cases:
+        rep, counts = engine.value_counts_str_host(cells)
+        got = {cells[int(r)]: int(c) for r, c in zip(rep, counts)}
+        assert got == dict(Counter(cells)) and len(rep) == len(got)
+    # mixed-type field still goes through the dictionary path and agrees with the oracle
+    db = utils.Database()
+    vals = ["1", 1, 1.0, None, "x", True, 2.5, "1"] * 50
+    db.insert_one_in_file("m", rsem.dataset_metadata("m", ["v", "t"]))
+    db.insert_many_in_file("m", [{"_id": i + 1, "v": v, "t": str(v)} for i, v in enumerate(vals)])
+    h = Histogram(db, utils.HistogramMetadata(db), engine)
+    h.create_file("m", "mh", ["v", "t"])
+    h.wait()
+    docs = db.find("m", {})
+    for d, f in zip(sorted((x for x in db.find("mh", {}) if x["_id"]), key=lambda x: x["_id"]), ["v", "t"]):
+        assert rsem.normalise_group_result(d[f]) == rsem.normalise_group_result(rsem.group_counts(docs, f))
