@@ -350,16 +350,26 @@ int lo_init(int device, lo_ctx **out) {
     ctx->device    = device;
     ctx->sm_count  = prop.multiProcessorCount;
     ctx->hbm_bytes = prop.totalGlobalMem;
-    LO_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    LO_CUDA(cudaStreamCreateWithFlags(&ctx->h2d, cudaStreamNonBlocking));
-    LO_CUDA(cudaStreamCreateWithFlags(&ctx->d2h, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; ++i) {
-        LO_CUDA(cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming));
-        LO_CUDA(cudaEventCreateWithFlags(&ctx->ev_k[i], cudaEventDisableTiming));
-        LO_CUDA(cudaEventCreateWithFlags(&ctx->ev_d2h[i], cudaEventDisableTiming));
+    ctx->stream = ctx->h2d = ctx->d2h = nullptr;
+    for (int i = 0; i < 2; ++i) ctx->ev_h2d[i] = ctx->ev_k[i] = ctx->ev_d2h[i] = nullptr;
+    auto setup = [&]() -> int {
+        LO_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        LO_CUDA(cudaStreamCreateWithFlags(&ctx->h2d, cudaStreamNonBlocking));
+        LO_CUDA(cudaStreamCreateWithFlags(&ctx->d2h, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            LO_CUDA(cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming));
+            LO_CUDA(cudaEventCreateWithFlags(&ctx->ev_k[i], cudaEventDisableTiming));
+            LO_CUDA(cudaEventCreateWithFlags(&ctx->ev_d2h[i], cudaEventDisableTiming));
+        }
+        return configure_kernels();
+    };
+    const int rc = setup();
+    if (rc != LO_OK) {              // keep the error message, release whatever was created
+        const std::string msg = g_err;
+        lo_shutdown(ctx);
+        g_err = msg;
+        return rc;
     }
-    int rc = configure_kernels();
-    if (rc != LO_OK) { delete ctx; return rc; }
     *out = ctx;
     return LO_OK;
 }
@@ -371,14 +381,14 @@ int lo_shutdown(lo_ctx *ctx) {
     for (int i = 0; i < 2; ++i) {
         if (ctx->stage_in[i]) cudaFree(ctx->stage_in[i]);
         if (ctx->stage_out[i]) cudaFree(ctx->stage_out[i]);
-        cudaEventDestroy(ctx->ev_h2d[i]);
-        cudaEventDestroy(ctx->ev_k[i]);
-        cudaEventDestroy(ctx->ev_d2h[i]);
+        if (ctx->ev_h2d[i]) cudaEventDestroy(ctx->ev_h2d[i]);
+        if (ctx->ev_k[i]) cudaEventDestroy(ctx->ev_k[i]);
+        if (ctx->ev_d2h[i]) cudaEventDestroy(ctx->ev_d2h[i]);
     }
     if (ctx->host_counts_dev) cudaFree(ctx->host_counts_dev);
-    cudaStreamDestroy(ctx->stream);
-    cudaStreamDestroy(ctx->h2d);
-    cudaStreamDestroy(ctx->d2h);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->h2d) cudaStreamDestroy(ctx->h2d);
+    if (ctx->d2h) cudaStreamDestroy(ctx->d2h);
     delete ctx;
     return LO_OK;
 }
