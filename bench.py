@@ -59,7 +59,9 @@ def peaks() -> tuple[float, str]:
 
 
 class ClockSampler:
-    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md 'clocks line')."""
+    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md 'clocks line').  The process is started
+    before the warm-up (nvidia-smi needs ~100 ms to come up); every line is stamped on receipt and only the
+    samples that fall inside [mark_start, mark_end] are summarised."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -67,11 +69,12 @@ class ClockSampler:
 
     def __init__(self, device: int):
         self.device, self.rows, self.proc, self.thread = device, [], None, None
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.device), "-lms", "50"], stdout=subprocess.PIPE,
+                                          "-i", str(self.device), "-lms", "100"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -81,29 +84,42 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def mark_start(self, wait_s: float = 2.0):
+        """Called right before the timed region; first makes sure nvidia-smi is actually producing lines."""
+        deadline = time.time() + wait_s
+        while self.proc is not None and not self.rows and time.time() < deadline:
+            time.sleep(0.01)
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self) -> dict:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.12)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, smax, reasons = [], [], set()
+        inside = [r for t, r in self.rows if self.t0 is not None and self.t0 <= t <= (self.t1 or t) + 0.1]
+        used = inside if inside else [r for _t, r in self.rows[-3:]]
+        sm, smax, power, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in used:
             try:
-                sm.append(float(r[1])); smax.append(float(r[2]))
+                sm.append(float(r[1])); smax.append(float(r[2])); power.append(float(r[3]))
             except Exception:
                 continue
             for nm, v in zip(names, r[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(power) if power else None, "samples": len(sm),
+                "samples_inside_timed_region": len(inside), "reasons": sorted(reasons)}
 
 
 # ======================================================================================================
@@ -263,6 +279,9 @@ def run_gpu(args) -> None:
         elif world > 1:
             allreduce_counts(counts_t)          # ONE ncclAllReduce of k*nbins int64 over NVLink, same stream
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         step(False)
     torch.cuda.synchronize()
@@ -281,9 +300,7 @@ def run_gpu(args) -> None:
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    sampler.mark_start()
     launches0 = eng.launch_count
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_start.record(stream)
@@ -291,6 +308,7 @@ def run_gpu(args) -> None:
         step(True)
     t_end.record(stream)
     torch.cuda.synchronize()
+    sampler.mark_end()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
