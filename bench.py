@@ -239,7 +239,6 @@ def run_gpu(args) -> None:
     # N > 1: "p2p" fuses the merge into the kernel's flush (system-scope REDs into rank 0's matrix over NVLink);
     # "nccl" is local counts + one all-reduce.  "auto" = p2p when the CUDA-IPC setup succeeds on every rank and a
     # probe step completes without a flag time-out, else nccl — both are GPU paths, the line says which ran.
-    side_stream = torch.cuda.Stream()
     peer, merge_note = None, "nccl"
     if world > 1 and args.merge in ("p2p", "auto"):
         from learningorchestra_b200.sharding import PeerReduce
@@ -276,7 +275,7 @@ def run_gpu(args) -> None:
             e1.record(stream)
             kev.append((e0, e1))
         if peer is not None:
-            peer.after_kernel(stream, side_stream)     # root's epilogue runs beside the next step's kernel
+            peer.after_kernel(stream)
         elif world > 1:
             allreduce_counts(counts_t)          # ONE ncclAllReduce of k*nbins int64 over NVLink, same stream
 

@@ -77,7 +77,6 @@ class PeerReduce:
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self.n = self.k * self.nbins
         self.step = 0
-        self._epilogue_done = [None, None]
         self.flags = engine.dev_alloc(self.FLAG_BYTES)
         self.local_counts = engine.dev_alloc(2 * self.n * 8) if self.rank == root else 0
         self.result = engine.dev_alloc(self.n * 8) if self.rank == root else 0
@@ -108,36 +107,20 @@ class PeerReduce:
         return self.engine.wrap_counts(self.k, self.nbins, buf)
 
     def before_kernel(self, stream=None):
-        done = self._epilogue_done[self.step % 2]
-        if self.rank == self.root and done is not None:
-            stream.wait_event(done)          # the side-stream epilogue of step-2 has re-zeroed this buffer
         if self.rank != self.root and self.step >= 2:
             self.engine.flag_wait(self.flags + self._CLEAN, self.step - 1, self.flags + self._TIMED_OUT,
                                   self.timeout_ms, stream)
 
-    def after_kernel(self, stream=None, side_stream=None):
-        """``side_stream`` (a ``torch.cuda.Stream``, root only): run the root's epilogue there so that it — and its
-        wait for the slowest rank — is off the critical path; the root's next kernel (other buffer) starts at once."""
+    def after_kernel(self, stream=None):
         eng = self.engine
         parity = self.step % 2
         eng.flag_add(self.root_flags + self._ARRIVED + 8 * parity, 1, stream)    # arrived[parity] += 1 on the root
         if self.rank == self.root:
             buf = self.counts_base + parity * self.n * 8
-            where = stream
-            if side_stream is not None:
-                import torch
-                ev = torch.cuda.Event()
-                ev.record(stream)
-                side_stream.wait_event(ev)
-                where = side_stream
             # one launch: wait for W arrivals, move the merged counts to `result`, re-zero, signal "clean"
             eng.peer_root_epilogue(self.flags + self._ARRIVED + 8 * parity, self.world * (self.step // 2 + 1),
                                    self.flags + self._TIMED_OUT, buf, self.result, self.n, self.peer_clean,
-                                   self.timeout_ms, where)
-            if side_stream is not None:
-                done = torch.cuda.Event()
-                done.record(side_stream)
-                self._epilogue_done[parity] = done
+                                   self.timeout_ms, stream)
         self.step += 1
 
     # -- results ----------------------------------------------------------------------------------------
