@@ -315,3 +315,17 @@ def test_gpu_hash_group_by_on_text_columns(engine):
     docs = db.find("m", {})
     for d, f in zip(sorted((x for x in db.find("mh", {}) if x["_id"]), key=lambda x: x["_id"]), ["v", "t"]):
         assert rsem.normalise_group_result(d[f]) == rsem.normalise_group_result(rsem.group_counts(docs, f))
+
+
+def test_builder_front_end_serves_resident_columns(engine):
+    from learningorchestra_b200.builder_frontend import file_processor
+    engine.resident.clear()
+    db = _titanic_db()
+    job = DataType(db, utils.DataTypeMetadata(db), engine)
+    job.convert_existent_file("titanic", {"Age": "number", "Fare": "number", "Survived": "number"})
+    job.wait()
+    host = file_processor(db, "titanic")
+    dev = file_processor(db, "titanic", engine)
+    assert host.equals(dev)
+    assert {"Age", "Fare", "Survived"} <= set(engine.resident.ensure(db, "titanic", ["Age"]).fields)
+    engine.resident.clear()

@@ -206,3 +206,20 @@ def test_gpu_jobs_fail_loudly_without_an_engine():
         h.wait()
     assert db.find_one("hh", {"_id": 0})["finished"] is False
     assert [d for d in db.find("hh", {}) if d["_id"] != 0] == []
+
+
+def test_builder_front_end_drops_metadata_columns():
+    """builder_image/builder.py:172-194: load -> filter(_id != 0) -> drop(metadata fields)."""
+    from learningorchestra_b200.builder_frontend import METADATA_FIELDS, file_processor
+    db = utils.Database()
+    _titanic_db(db)
+    gold = _load("reference_datatype_number.json")
+    db.update_by_id("titanic", {row[0]: dict(zip(gold["fields"], row[1:])) for row in gold["rows"]})
+    t = file_processor(db, "titanic")
+    assert t.num_rows == 891 and not set(t.column_names) & set(METADATA_FIELDS)
+    assert t.column_names == [f for f in rsem.TITANIC_HEADERS if f not in METADATA_FIELDS]
+    import pyarrow as pa
+    assert t.schema.field("Survived").type == pa.int64() and t.schema.field("Fare").type == pa.float64()
+    assert t.schema.field("Name").type == pa.string()
+    ages = t.column("Age").to_pylist()
+    assert ages == [row[3] for row in gold["rows"]] and ages.count(None) == 176
