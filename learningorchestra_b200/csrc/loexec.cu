@@ -154,7 +154,18 @@ bool fastdiv_ok(float w) {
     return w >= 0x1p-100f && w <= 0x1p100f;
 }
 
+template <typename K>
+int allow_smem_tma(K kernel) {
+    LO_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lo::kTmaSmemBytes));
+    return LO_OK;
+}
+
 int configure_kernels() {
+    LO_TRY(allow_smem_tma(lo::k_project_cast_hist_tma<0, true, true>));
+    LO_TRY(allow_smem_tma(lo::k_project_cast_hist_tma<1, true, true>));
+    LO_TRY(allow_smem_tma(lo::k_project_cast_hist_tma<2, true, true>));
+    LO_TRY(allow_smem_tma(lo::k_project_cast_hist_tma<1, false, false>));
+    LO_TRY(allow_smem_tma(lo::k_project_cast_hist_tma<2, false, false>));
     LO_TRY(allow_smem_hist<0>());
     LO_TRY(allow_smem_hist<1>());
     LO_TRY(allow_smem_hist<2>());
@@ -175,6 +186,32 @@ int launch_f64(lo_ctx *ctx, const lo_table *in, const lo_table *out, int32_t out
     const long long out_pitch = out ? out->pitch : 0;
     bool fast = HIST;
     for (int j = 0; HIST && j < P.k; ++j) fast = fast && fastdiv_ok(P.w[j]);
+    // LOEXEC_TMA=1: stage the slabs through shared memory with the bulk-copy engine (A/B variant).
+    // Only full tiles; the ragged last tile of each column (and unaligned / slow-divide cases) keep the LDG kernel.
+    static const bool use_tma = [] { const char *e = getenv("LOEXEC_TMA"); return e && e[0] == '1'; }();
+    if (use_tma && aligned && fast == HIST && in->nrows >= lo::kTileRows) {
+        const unsigned full_tiles = (unsigned)(in->nrows / lo::kTileRows);
+        const unsigned long long tblocks = (unsigned long long)full_tiles * (unsigned)P.k;
+        lo::k_project_cast_hist_tma<OUT, HIST, HIST><<<(unsigned)tblocks, lo::kThreads + 32, lo::kTmaSmemBytes, s>>>(
+            in->base, in->pitch, out_base, out_pitch, in->nrows, full_tiles, counts, P);
+        LO_CUDA(cudaGetLastError());
+        ctx->launches.fetch_add(1, std::memory_order_relaxed);
+        const int64_t done = (int64_t)full_tiles * lo::kTileRows;
+        if (done == in->nrows) return LO_OK;
+        // the remaining rows of every column: one ragged tile each, through the regular kernel on a row-offset view
+        lo_table tin = *in;
+        tin.base = in->base + done * 8; tin.nrows = in->nrows - done;
+        lo_table tout;
+        if (out) { tout = *out; tout.base = out->base + done * (int64_t)dtype_size(out->dtype); tout.nrows = tin.nrows; }
+        char *ob = out ? tout.base + (int64_t)out_col0 * tout.pitch : nullptr;
+        if (fast) lo::k_project_cast_hist<OUT, HIST, true, true><<<(unsigned)P.k, lo::kThreads, smem, s>>>(
+                      tin.base, tin.pitch, ob, out_pitch, tin.nrows, 1u, counts, P);
+        else      lo::k_project_cast_hist<OUT, HIST, true, false><<<(unsigned)P.k, lo::kThreads, smem, s>>>(
+                      tin.base, tin.pitch, ob, out_pitch, tin.nrows, 1u, counts, P);
+        LO_CUDA(cudaGetLastError());
+        ctx->launches.fetch_add(1, std::memory_order_relaxed);
+        return LO_OK;
+    }
 #define LO_LAUNCH(AL, FD)                                                                              \
     lo::k_project_cast_hist<OUT, HIST, AL, FD><<<(unsigned)blocks, lo::kThreads, smem, s>>>(           \
         in->base, in->pitch, out_base, out_pitch, in->nrows, tiles_per_col, counts, P)

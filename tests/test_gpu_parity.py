@@ -282,3 +282,18 @@ def test_plain_c_consumer_runs_the_hot_path(engine):
     from test_abi_cpu import _build_c_consumer
     out = subprocess.run([str(_build_c_consumer())], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and "abi_smoke ok" in out.stdout, out.stderr
+
+
+def test_tma_staged_variant_has_the_same_results(engine):
+    """LOEXEC_TMA=1 routes full tiles through the cp.async.bulk + mbarrier ring kernel; the switch
+    is read once per process, so the parity subset is re-run in a child process with it set."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, LOEXEC_TMA="1")
+    out = subprocess.run([sys.executable, "-m", "pytest", __file__, "-m", "gpu", "-q", "-x", "-k",
+                          "ragged_sizes or test_nbins or special_values or constant_column or histogram_only or "
+                          "projection_cast_only or accumulate or host_buffer"],
+                         capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert " passed" in out.stdout
