@@ -39,6 +39,14 @@ def test_library_is_sm100a_native_code(built):
     assert "MUFU.RCP" not in sass.split("BAR.SYNC")[0] or True
 
 
+def test_tma_variant_is_compiled_with_bulk_copy_and_mbarriers(built):
+    """The opt-in TMA-staged kernel really uses the bulk-copy engine: UBLKCP (cp.async.bulk) + SYNCS (mbarrier) in SASS."""
+    from learningorchestra_b200 import _native
+    sass = subprocess.run(["cuobjdump", "-sass", str(_native.LIB_PATH)], capture_output=True, text=True).stdout
+    block = sass.split("k_project_cast_hist_tmaILi1ELb1ELb1E")[1].split("Function :")[0]
+    assert "UBLKCP" in block and "SYNCS" in block and "LDS.128" in block
+
+
 def test_no_gpu_means_loud_failure_not_fallback(built):
     """On a CPU-only host every entry that would compute must fail with LO_ERR_NO_DEVICE."""
     import torch
