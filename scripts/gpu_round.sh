@@ -21,3 +21,8 @@ if [[ "$*" == *u8ncu* ]]; then
       -o gpurun_out/prof_u8_$TAG -f python scripts/kbench.py 1000000 8 > gpurun_out/ncu_u8_$TAG.log 2>&1
   tail -2 gpurun_out/ncu_u8_$TAG.log
 fi
+if [[ "$*" == *tmancu* ]]; then
+  LOEXEC_TMA=1 timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_project_cast_hist_tma -s 3 -c 1 \
+      -o gpurun_out/prof_tma_$TAG -f python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu > gpurun_out/ncu_tma_$TAG.log 2>&1
+  tail -2 gpurun_out/ncu_tma_$TAG.log
+fi
