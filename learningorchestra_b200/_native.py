@@ -66,6 +66,7 @@ SIGNATURES = {
     "lo_shutdown": (C.c_int, [_P]),
     "lo_ctx_device": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
     "lo_sync": (C.c_int, [_P, _P]),
+    "lo_set_tma": (C.c_int, [_P, C.c_int]),
     "lo_launch_count": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "lo_host_alloc": (C.c_int, [_P, C.c_size_t, C.POINTER(_P)]),
     "lo_host_free": (C.c_int, [_P, _P]),

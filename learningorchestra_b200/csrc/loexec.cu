@@ -77,6 +77,7 @@ struct lo_ctx {
     cudaStream_t stream;       // default stream for NULL `stream` arguments
     cudaStream_t h2d, d2h;     // copy streams of the *_host pipeline
     std::atomic<int64_t> launches{0};
+    std::atomic<bool> use_tma{false};   // LOEXEC_TMA=1 or lo_set_tma(): stage slabs through smem with cp.async.bulk
     // *_host pipeline staging (one pipeline at a time per context)
     std::mutex   host_mu;
     char        *stage_in[2]  = {nullptr, nullptr};
@@ -188,8 +189,7 @@ int launch_f64(lo_ctx *ctx, const lo_table *in, const lo_table *out, int32_t out
     for (int j = 0; HIST && j < P.k; ++j) fast = fast && fastdiv_ok(P.w[j]);
     // LOEXEC_TMA=1: stage the slabs through shared memory with the bulk-copy engine (A/B variant).
     // Only full tiles; the ragged last tile of each column (and unaligned / slow-divide cases) keep the LDG kernel.
-    static const bool use_tma = [] { const char *e = getenv("LOEXEC_TMA"); return e && e[0] == '1'; }();
-    if (use_tma && aligned && fast == HIST && in->nrows >= lo::kTileRows) {
+    if (ctx->use_tma.load(std::memory_order_relaxed) && aligned && fast == HIST && in->nrows >= lo::kTileRows) {
         const unsigned full_tiles = (unsigned)(in->nrows / lo::kTileRows);
         const unsigned long long tblocks = (unsigned long long)full_tiles * (unsigned)P.k;
         lo::k_project_cast_hist_tma<OUT, HIST, HIST><<<(unsigned)tblocks, lo::kThreads + 32, lo::kTmaSmemBytes, s>>>(
@@ -400,6 +400,7 @@ int lo_init(int device, lo_ctx **out) {
         }
         return configure_kernels();
     };
+    if (const char *e = getenv("LOEXEC_TMA")) ctx->use_tma.store(e[0] == '1');
     const int rc = setup();
     if (rc != LO_OK) {              // keep the error message, release whatever was created
         const std::string msg = g_err;
@@ -441,6 +442,12 @@ int lo_ctx_device(const lo_ctx *ctx, int *device, int *sm_count, size_t *hbm_byt
 int lo_sync(lo_ctx *ctx, void *stream) {
     LO_TRY(check_ctx(ctx));
     LO_CUDA(cudaStreamSynchronize(pick(ctx, stream)));
+    return LO_OK;
+}
+
+int lo_set_tma(lo_ctx *ctx, int enabled) {
+    if (!ctx) return fail(LO_ERR_INVALID, "ctx is NULL");
+    ctx->use_tma.store(enabled != 0, std::memory_order_relaxed);
     return LO_OK;
 }
 
