@@ -86,11 +86,15 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def mark_start(self, wait_s: float = 2.0):
-        """Called right before the timed region; first makes sure nvidia-smi is actually producing lines."""
+    def wait_ready(self, wait_s: float = 2.0):
+        """Block until nvidia-smi is actually producing lines.  Must be called BEFORE the barrier that precedes
+        the timed region: only rank 0 samples, and waiting after the barrier would let the other ranks start
+        their timed steps and then sit in the merge waiting for rank 0."""
         deadline = time.time() + wait_s
         while self.proc is not None and not self.rows and time.time() < deadline:
             time.sleep(0.01)
+
+    def mark_start(self):
         self.t0 = time.time()
 
     def mark_end(self):
@@ -297,6 +301,7 @@ def run_gpu(args) -> None:
             for _ in range(args.warmup):
                 step(False)
             torch.cuda.synchronize()
+    sampler.wait_ready()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
