@@ -213,12 +213,13 @@ def run_gpu(args) -> None:
         if world == 1 and args.gpus > 1:
             raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
         args.gpus = world
-    if rank == 0:
-        build_native()
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        dist.barrier()
+    if rank == 0:
+        build_native()                      # no-op when the in-tree .so is newer than its sources
+    if world > 1:
+        dist.barrier()                      # nobody loads libloexec.so while rank 0 might be rewriting it
 
     eng = Engine(local_rank)
     ncols, total_rows = args.cols, args.rows

@@ -45,17 +45,21 @@ def _stale(target: Path, sources: list[Path]) -> bool:
 
 
 def build_native(force: bool = False, verbose: bool = False) -> Path:
-    sources = [CSRC / "loexec.cu", CSRC / "kernels.cuh", ROOT / "include" / "loexec.h"]
+    sources = [CSRC / "loexec.cu", CSRC / "kernels.cuh", CSRC / "parse_number.cuh", CSRC / "pow5_table.inc",
+               ROOT / "include" / "loexec.h"]
     if not force and not _stale(LIB_PATH, sources):
         return LIB_PATH
     LIB_DIR.mkdir(parents=True, exist_ok=True)
     cmd = [_nvcc(), *NVCC_FLAGS, "-I", str(ROOT / "include"), "-I", str(CSRC)]
     if verbose:
         cmd += ["-Xptxas", "-v"]
-    cmd += ["-o", str(LIB_PATH), str(CSRC / "loexec.cu")]
+    tmp = LIB_PATH.with_suffix(f".so.tmp{os.getpid()}")
+    cmd += ["-o", str(tmp), str(CSRC / "loexec.cu")]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
+        tmp.unlink(missing_ok=True)
         raise RuntimeError(f"nvcc failed:\n{' '.join(cmd)}\n{proc.stdout}\n{proc.stderr}")
+    os.replace(tmp, LIB_PATH)               # atomic: a concurrent loader sees the old or the new file, never half
     if verbose:
         print(proc.stderr, file=sys.stderr)
     return LIB_PATH
@@ -67,11 +71,14 @@ def build_oracle(force: bool = False) -> Path:
     ORACLE_LIB.parent.mkdir(parents=True, exist_ok=True)
     # -ffp-contract=off: the oracle's fp32/fp64 arithmetic must be one IEEE operation per
     # C operator (no FMA fusion), -fno-fast-math is the default and stays.
+    tmp = ORACLE_LIB.with_suffix(f".so.tmp{os.getpid()}")
     cmd = ["gcc", "-O2", "-std=c11", "-fPIC", "-shared", "-fopenmp", "-ffp-contract=off",
-           "-Wall", "-o", str(ORACLE_LIB), str(ORACLE_SRC), "-lm"]
+           "-Wall", "-o", str(tmp), str(ORACLE_SRC), "-lm"]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
+        tmp.unlink(missing_ok=True)
         raise RuntimeError(f"gcc failed:\n{' '.join(cmd)}\n{proc.stdout}\n{proc.stderr}")
+    os.replace(tmp, ORACLE_LIB)
     return ORACLE_LIB
 
 
