@@ -82,3 +82,97 @@ def test_c_and_numpy_oracles_agree_on_arbitrary_inputs(x, lo, span, nbins):
     if not (np.isfinite(w) and w > 0):
         return
     assert np.array_equal(cport.hist_f32(f_c, lo, hi, nbins), bn.hist_f32(f_n, lo, hi, nbins))
+
+
+# ---- executors' adapter logic on machine-generated documents (oracle-backed test double for the Engine) ------------
+_cell = st.one_of(st.none(), st.integers(-50, 50), st.floats(-5, 5, allow_nan=False).map(lambda x: round(x, 1)),
+                  st.sampled_from(["", "a", "b", "1", "1.0", " x"]), st.booleans())
+_column_kinds = st.sampled_from(["ints", "floats", "text", "mixed", "sparse"])
+
+
+def _column(kind, n, draw):
+    if kind == "ints":
+        return draw(st.lists(st.one_of(st.none(), st.integers(-3, 3)), min_size=n, max_size=n))
+    if kind == "floats":
+        return draw(st.lists(st.one_of(st.none(), st.sampled_from([0.0, -0.0, 1.5, 2.0, float("nan"), 1e300, -7.25])), min_size=n, max_size=n))
+    if kind == "text":
+        return draw(st.lists(st.one_of(st.none(), st.sampled_from(["", "a", "b", "ab", "é", "1"])), min_size=n, max_size=n))
+    if kind == "sparse":
+        return draw(st.lists(st.sampled_from([None, "MISSING", 1, "x"]), min_size=n, max_size=n))
+    return draw(st.lists(_cell, min_size=n, max_size=n))
+
+
+@st.composite
+def _collections(draw):
+    n = draw(st.integers(0, 30))
+    kinds = draw(st.lists(_column_kinds, min_size=1, max_size=4))
+    cols = {f"f{i}": _column(kd, n, draw) for i, kd in enumerate(kinds)}
+    docs = []
+    for r in range(n):
+        d = {"_id": r + 1}
+        for f, vals in cols.items():
+            if vals[r] != "MISSING":            # a missing key groups with null, like in MongoDB
+                d[f] = vals[r]
+        docs.append(d)
+    return list(cols), docs
+
+
+@settings(max_examples=300, deadline=None)
+@given(data=_collections())
+def test_histogram_executor_equals_group_semantics_on_arbitrary_documents(data):
+    from learningorchestra_b200 import utils
+    from learningorchestra_b200.histogram import Histogram
+    from oracle_engine import OracleEngine
+    fields, docs = data
+    db = utils.Database()
+    db.insert_one_in_file("d", rsem.dataset_metadata("d", fields))
+    db.insert_many_in_file("d", docs)
+    job = Histogram(db, utils.HistogramMetadata(db), OracleEngine())
+    job.create_file("d", "h", list(fields))
+    job.wait()
+    meta = db.find_one("h", {"_id": 0})
+    assert meta["finished"] is True and meta["fields"] == fields
+    results = sorted((x for x in db.find("h", {}) if x["_id"] != 0), key=lambda x: x["_id"])
+    everything = db.find("d", {})                # metadata document included, as in the reference's pipeline
+    assert [x["_id"] for x in results] == list(range(1, len(fields) + 1))
+    for res, f in zip(results, fields):
+        assert rsem.normalise_group_result(res[f]) == rsem.normalise_group_result(rsem.group_counts(everything, f)), f
+
+
+@settings(max_examples=200, deadline=None)
+@given(cells=st.lists(st.one_of(st.none(), st.sampled_from(["", "1", "2.5", " 3 ", "1e2", "-0.0", "nan", "1_0"]),
+                                st.integers(-5, 5), st.floats(-2, 2, allow_nan=False), st.booleans()), max_size=25),
+       poison=st.one_of(st.none(), st.integers(0, 24)))
+def test_datatype_number_equals_the_reference_loop_on_arbitrary_cells(cells, poison):
+    """The adapter around the GPU parser keeps the reference's per-document semantics, including where it stops."""
+    from learningorchestra_b200 import utils
+    from learningorchestra_b200.data_type_update import DataType
+    from oracle_engine import OracleEngine
+    cells = list(cells)
+    if poison is not None and poison < len(cells):
+        cells[poison] = "abc"
+    docs = [{"_id": i + 1, "v": c} for i, c in enumerate(cells)]
+    db = utils.Database()
+    db.insert_one_in_file("t", rsem.dataset_metadata("t", ["v"]))
+    db.insert_many_in_file("t", docs)
+    expected, failed = [dict(d) for d in docs], False
+    for d in expected:                               # the reference's loop (oracle restatement), stopping at a ValueError
+        try:
+            changed, v = rsem.convert_value(d["v"], "number")
+        except ValueError:
+            failed = True
+            break
+        if changed:
+            d["v"] = v
+    job = DataType(db, utils.DataTypeMetadata(db), OracleEngine())
+    job.convert_existent_file("t", {"v": "number"})
+    if failed:
+        with pytest.raises(ValueError):
+            job.wait()
+    else:
+        job.wait()
+    got = sorted((d for d in db.find("t", {}) if d["_id"] != 0), key=lambda d: d["_id"])
+    for g, e in zip(got, expected):
+        same = (g["v"] == e["v"] and type(g["v"]) is type(e["v"])) or (isinstance(g["v"], float) and g["v"] != g["v"] and e["v"] != e["v"])
+        assert same, (g, e)
+    assert db.find_one("t", {"_id": 0})["finished"] is (not failed)
