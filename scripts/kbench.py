@@ -48,6 +48,13 @@ def main():
     m, b = timeit(lambda: eng.hist_u8_cols(tu, range(784), counts=c8, stream=stream), stream); rep("hist_u8 1Mx784", m, b, 784e6)
     tu2 = eng.table("u8", 8_000_000, 784).fill_synthetic(3, 20260921, stream=stream)
     m, b = timeit(lambda: eng.hist_u8_cols(tu2, range(784), counts=c8, stream=stream), stream); rep("hist_u8 8Mx784", m, b, 8 * 784e6)
+    rng = np.random.default_rng(3)
+    dense = eng.table("u8", 4_000_000, 128)
+    blk = rng.integers(0, 256, 4_000_000, dtype=np.uint8)
+    for c in range(128):
+        dense.upload(c, np.roll(blk, c * 977))
+    c128 = eng.counts(128, 256)
+    m, b = timeit(lambda: eng.hist_u8_cols(dense, range(128), counts=c128, stream=stream), stream); rep("hist_u8 dense random 4Mx128", m, b, 128 * 4e6)
     Path("gpurun_out").mkdir(exist_ok=True)
     Path("gpurun_out/kbench.json").write_text(json.dumps(res, indent=1))
 
