@@ -152,3 +152,22 @@ class App:
 
 def create_app(database: Database | None = None, engine=None, synchronous: bool = False) -> App:
     return App(database or Database(), engine, synchronous)
+
+
+def main() -> None:
+    """``python -m learningorchestra_b200.server``: the three hot-path routes on one werkzeug dev server (the reference
+    runs three Flask processes with ``app.run(host, port)``, e.g. ``projection_image/server.py:157-161``).
+    LOEXEC_HOST / LOEXEC_PORT / LOEXEC_DEVICE select the bind address and the GPU."""
+    import os
+
+    from werkzeug.serving import run_simple
+
+    from .engine import Engine
+
+    engine = Engine(int(os.environ.get("LOEXEC_DEVICE", "0")))          # fails loudly without a B200
+    app = create_app(Database(), engine)
+    run_simple(os.environ.get("LOEXEC_HOST", "127.0.0.1"), int(os.environ.get("LOEXEC_PORT", "5001")), app, threaded=True)
+
+
+if __name__ == "__main__":
+    main()
