@@ -79,3 +79,26 @@ def dictionary_encode(values):
             reps.append(v)
         codes[i] = c
     return codes, reps
+
+
+def tagged_cell(value) -> bytes:
+    """Byte encoding under which two cells are equal exactly when MongoDB's ``$group`` puts them in one group
+    (:func:`group_key`): lets ONE byte-wise GPU group-by handle a field that mixes text, numbers and booleans."""
+    import struct
+    kind = group_key(value)
+    if kind[0] == "str":
+        return b"s" + value.encode("utf-8")
+    if kind[0] == "bool":
+        return b"b1" if value else b"b0"
+    if kind[0] == "num":
+        v = kind[1]
+        if v == "nan":
+            return b"n" + struct.pack("<Q", 0x7FF8000000000000)
+        if v in ("inf", "-inf"):
+            return b"n" + struct.pack("<d", float(v))
+        if isinstance(v, int):
+            if abs(v) <= _EXACT_INT:
+                return b"n" + struct.pack("<d", float(v))      # 1 and 1.0 (and -0.0 / 0.0 -> int 0) meet here
+            return b"I" + str(v).encode("ascii")               # beyond 2^53: exact decimal text
+        return b"n" + struct.pack("<d", v)
+    return b"o" + kind[1].encode("utf-8")

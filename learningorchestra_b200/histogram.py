@@ -5,15 +5,19 @@ Reference job (``histogram.py:25-44``): per requested field one MongoDB pipeline
 document included: it has no such field, so it lands in — and inflates — the ``null`` group), one result
 document ``{field: [{"_id": value, "count": n}, ...], "_id": k}`` per field, then ``finished: True``.
 
-Here the counting runs on the GPU.  Number fields (every value an int / float / None) are grouped by a GPU
-hash table on the binary64 keys (``lo_value_counts_f64_host``), text fields (every value a ``str`` / None) by a
-GPU hash table on the cells' bytes (``lo_value_counts_str_host``) — no host dictionary in either case.  For
-the remaining (mixed-type) fields the adapter dictionary-encodes the values (MongoDB's grouping equality,
-:func:`columnar.group_key`) into dense codes; fields with <= 256 distinct keys are packed into byte columns
-and counted together by ``k_hist_u8_cols`` (per-thread byte-counter histograms, ``lo_hist_u8_cols_host``),
-larger dictionaries by ``k_count_codes_u32`` (``lo_value_counts_u32_host``).  With ``bins`` (optional extension, REST key ``bins`` / ``range``) the
-fields must be numeric and get the fixed-width B-semantics histogram of SURVEY.md §8c from the fused
-kernel instead.
+Here the counting runs on the GPU with no host dictionary:
+
+* number fields (every value an int / float / None): GPU hash group-by on the binary64 keys
+  (``lo_value_counts_f64_host``; -0.0 == 0.0, NaN == NaN as in MongoDB);
+* text fields (every value a ``str`` / None): GPU hash group-by on the cells' bytes (``lo_value_counts_str_host``);
+* mixed-type fields: the same byte-wise group-by over a tagged encoding under which two cells are equal exactly
+  when MongoDB groups them (:func:`columnar.tagged_cell`: 1 == 1.0, ``True`` != 1, ``"1"`` != 1).
+
+``None`` / missing values (the metadata document among them) are counted while packing.  With ``bins`` (optional
+extension, REST keys ``bins`` / ``range``) the fields must be numeric and get the fixed-width B-semantics histogram
+of SURVEY.md §8c from the fused kernel, run on the HBM-resident copy of the dataset (``table_cache``).
+The dictionary-code kernels (``hist_u8_cols_host`` / ``value_counts_u32_host``) remain available on the engine for
+columns that arrive already encoded (e.g. the uint8 tables of config M).
 """
 from __future__ import annotations
 
@@ -67,42 +71,26 @@ class Histogram:
     # ---- R-semantics: exact value counts -------------------------------------------------------------
     def __value_counts(self, documents, fields):
         results = {}
-        text_fields = []
         for f in fields:
             values = [d.get(f) for d in documents]
+            present = [i for i, v in enumerate(values) if v is not None]
             packed = columnar.numeric_column(values) if documents else None
-            if packed is None and documents and all(v is None or isinstance(v, str) for v in values):
-                cells = [v for v in values if v is not None]           # text field: hash group-by on the bytes
+            if not present:
+                groups = []
+            elif packed is not None:                                     # number field: group-by on binary64 keys
+                col, valid, kind = packed
+                keys, counts = self.engine.value_counts_f64_host(col[valid])
+                groups = [{"_id": (int(k) if kind == "int" else float(k)), "count": int(c)} for k, c in zip(keys, counts)]
+            else:                                                        # text or mixed: group-by on the cells' bytes
+                if all(isinstance(values[i], str) for i in present):
+                    cells = [values[i] for i in present]
+                else:
+                    cells = [columnar.tagged_cell(values[i]) for i in present]
                 rep, counts = self.engine.value_counts_str_host(cells)
-                groups = [{"_id": cells[int(r)], "count": int(c)} for r, c in zip(rep, counts)]
-                if len(cells) != len(values):
-                    groups.append({"_id": None, "count": len(values) - len(cells)})
-                results[f] = groups
-                continue
-            if packed is None:
-                text_fields.append(f)
-                continue
-            col, valid, kind = packed                      # number field: hash group-by on the device
-            keys, counts = self.engine.value_counts_f64_host(col[valid])
-            groups = [{"_id": (int(k) if kind == "int" else float(k)), "count": int(c)} for k, c in zip(keys, counts)]
-            nulls = int((~valid).sum())                    # None / missing (the metadata document among them)
-            if nulls:
-                groups.append({"_id": None, "count": nulls})
+                groups = [{"_id": values[present[int(r)]], "count": int(c)} for r, c in zip(rep, counts)]
+            if len(present) != len(values):                              # None / missing (metadata document included)
+                groups.append({"_id": None, "count": len(values) - len(present)})
             results[f] = groups
-        encoded = {f: columnar.dictionary_encode([d.get(f) for d in documents]) for f in text_fields}
-        small = [f for f in text_fields if len(encoded[f][1]) <= 256]
-        if small and documents:
-            cols = [encoded[f][0].astype(np.uint8) for f in small]
-            counts, _ = self.engine.hist_u8_cols_host(cols)
-            for j, f in enumerate(small):
-                reps = encoded[f][1]
-                results[f] = [{"_id": reps[c], "count": int(counts[j][c])} for c in range(len(reps))]
-        for f in text_fields:
-            if f in results:
-                continue
-            codes, reps = encoded[f]
-            counts = self.engine.value_counts_u32_host(codes, max(len(reps), 1)) if len(codes) else []
-            results[f] = [{"_id": reps[c], "count": int(counts[c])} for c in range(len(reps))]
         return results
 
     # ---- B-semantics: fixed-width bins of the fp32-cast value -----------------------------------------
