@@ -67,6 +67,12 @@ class DeviceCounts:
             N.check(self.engine._lib.lo_counts_free(self.engine._ctx, self._ptr))
         self._ptr = None
 
+    def __del__(self):          # best effort: device memory of a forgotten handle goes back when it is collected
+        try:
+            self.free()
+        except Exception:
+            pass
+
 
 class DeviceTable:
     """Columnar table in HBM: ``ncols`` slabs of ``nrows`` elements of one dtype."""
@@ -106,6 +112,12 @@ class DeviceTable:
         if self._h is not None and self.engine._ctx is not None:
             N.check(self.engine._lib.lo_table_free(self.engine._ctx, self._h))
         self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 class Engine:
