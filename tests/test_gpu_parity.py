@@ -297,3 +297,25 @@ def test_tma_staged_variant_has_the_same_results(engine):
                          capture_output=True, text=True, timeout=600, env=env)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert " passed" in out.stdout
+
+
+def test_more_projected_columns_than_one_launch_holds(engine):
+    """k > 128 (f64) and k > 1024 (u8) are split over several launches; counts / outputs line up per column."""
+    table = bn.synth_table_f64(1, SEED + 21, 7, 0, 70_000)
+    cols = [(3 * j + 1) % 7 for j in range(300)]
+    lo = np.linspace(-1000, -900, 300).astype(np.float32)
+    hi = np.linspace(900, 1000, 300).astype(np.float32)
+    t = engine.table_from_numpy(table)
+    out = engine.table("f32", 70_000, 300)
+    got = engine.project_cast_hist(t, cols, 100, lo, hi, out=out).to_numpy()
+    exp_out, exp = bn.project_cast_hist(table, cols, 100, lo, hi)
+    np.testing.assert_array_equal(got, exp)
+    for j in (0, 127, 128, 129, 255, 256, 299):
+        np.testing.assert_array_equal(_bits(out.to_numpy(j)), _bits(exp_out[j]))
+    out.free(); t.free()
+    tb = bn.synth_table_u8(SEED, 1300, 0, 5000)
+    t8 = engine.table_from_numpy(tb)
+    idx = list(range(1300)) + [5, 700]
+    got8 = engine.hist_u8_cols(t8, idx).to_numpy()
+    np.testing.assert_array_equal(got8, bn.hist_u8_cols(tb, idx))
+    t8.free()
