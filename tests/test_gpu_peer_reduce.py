@@ -60,15 +60,19 @@ def test_peer_reduce_equals_oracle(built, world):
     from oracle import cport
     total_rows, ncols, nbins, steps = 700_001, 4, 256, 5
     ctx = mp.get_context("spawn")
-    ret = ctx.SimpleQueue()
+    ret = ctx.Queue()
     port = _free_port()
     procs = [ctx.Process(target=_worker, args=(r, world, port, total_rows, ncols, nbins, steps, ret)) for r in range(world)]
     for p in procs:
         p.start()
-    results, timed_out = ret.get()
-    for p in procs:
-        p.join(timeout=120)
-        assert p.exitcode == 0
+    try:
+        results, timed_out = ret.get(timeout=240)       # never block forever if a worker died
+    finally:
+        for p in procs:
+            p.join(timeout=60)
+            if p.is_alive():
+                p.kill()
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
     assert timed_out == 0
     lo = np.full(ncols, -1000.0, np.float32)
     hi = np.full(ncols, 1000.0, np.float32)

@@ -57,15 +57,19 @@ def test_counts_allreduce_over_gloo(built, world):
     from oracle import cport
     total_rows, ncols, nbins = 250_007, 4, 256
     ctx = mp.get_context("spawn")
-    ret = ctx.SimpleQueue()
+    ret = ctx.Queue()
     port = _free_port()
     procs = [ctx.Process(target=_worker, args=(r, world, port, total_rows, ncols, nbins, ret)) for r in range(world)]
     for p in procs:
         p.start()
-    got = ret.get()
-    for p in procs:
-        p.join(timeout=120)
-        assert p.exitcode == 0
+    try:
+        got = ret.get(timeout=240)                       # never block forever if a worker died
+    finally:
+        for p in procs:
+            p.join(timeout=60)
+            if p.is_alive():
+                p.kill()
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
     lo = np.full(ncols, -1000.0, np.float32)
     hi = np.full(ncols, 1000.0, np.float32)
     exp, _ = cport.synth_project_cast_hist(1, SEED, 0, total_rows, -1000.0, 1000.0, list(range(ncols)), nbins, lo, hi)
