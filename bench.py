@@ -337,23 +337,38 @@ def run_gpu(args) -> None:
 
     # ---- end to end: host buffers in, host buffers out, through the plugin-facing C-ABI call ----------
     e2e = None
+    e2e_ready = False
     if not args.no_e2e:
+        import ctypes as C
         import psutil
+        from learningorchestra_b200 import _native as N
         avail = psutil.virtual_memory().available
         per_row = 12 * k
-        local_world = world
-        budget_rows = int(avail * 0.45 / local_world / per_row)
+        budget_rows = int(avail * 0.45 / world / per_row)
         e2e_rows = min(nrows, args.e2e_rows if args.e2e_rows else nrows, budget_rows)
         e2e_rows = max(61440, e2e_rows // 61440 * 61440) if e2e_rows >= 61440 else e2e_rows
-        hin = eng.pinned_empty((k, e2e_rows), np.float64)
-        hout = eng.pinned_empty((k, e2e_rows), np.float32)
-        import ctypes as C
-        from learningorchestra_b200 import _native as N
-        for j in range(k):   # host inputs = the projected columns of this rank's shard (device -> pinned host, untimed)
-            N.check(eng._lib.lo_table_download_col(eng._ctx, table._h, cols[j], 0, hin[j].ctypes.data_as(C.c_void_p), e2e_rows))
-        in_cols = [hin[j] for j in range(k)]
-        out_cols = [hout[j] for j in range(k)]
-        eng.project_cast_hist_host(in_cols, NBINS, lo, hi, out=out_cols)      # warm-up (allocates staging)
+        # set-up (pinned host buffers, staging) can fail on a box with little free RAM: every rank reports, and e2e
+        # is skipped on ALL ranks together rather than leaving some of them waiting in a collective
+        setup_error = None
+        try:
+            hin = eng.pinned_empty((k, e2e_rows), np.float64)
+            hout = eng.pinned_empty((k, e2e_rows), np.float32)
+            for j in range(k):   # host inputs = the projected columns of this rank's shard (device -> pinned host, untimed)
+                N.check(eng._lib.lo_table_download_col(eng._ctx, table._h, cols[j], 0, hin[j].ctypes.data_as(C.c_void_p), e2e_rows))
+            in_cols = [hin[j] for j in range(k)]
+            out_cols = [hout[j] for j in range(k)]
+            eng.project_cast_hist_host(in_cols, NBINS, lo, hi, out=out_cols)      # warm-up (allocates staging)
+        except Exception as exc:          # noqa: BLE001
+            setup_error = repr(exc)
+            log(f"[rank {rank}] e2e set-up failed: {setup_error}")
+        okf = torch.tensor([0.0 if setup_error else 1.0], device="cuda")
+        if world > 1:
+            dist.all_reduce(okf, op=dist.ReduceOp.MIN)
+        e2e_ready = float(okf[0]) == 1.0
+        if not e2e_ready:
+            e2e = {"value": None, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                   "error": setup_error or "set-up failed on another rank"}
+    if e2e_ready:
         if world > 1:
             dist.barrier()
         e2e_steps = max(1, min(args.steps, args.e2e_steps))
