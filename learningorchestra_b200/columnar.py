@@ -22,7 +22,43 @@ def data_rows(documents):
 def numeric_column(values):
     """(float64 array with NaN at nulls, valid mask, kind) or None if the column is not numeric.
     kind "int": every non-null value is an int that float64 holds exactly; "float": ints and floats mixed
-    (what the Mongo-Spark connector's schema inference widens to double)."""
+    (what the Mongo-Spark connector's schema inference widens to double).
+
+    Large columns are classified and packed by Arrow's C++ type inference; anything it does not take
+    (mixed bool / int, huge ints, exotic objects) falls through to the per-value loop, which is the definition."""
+    if len(values) >= 64:
+        fast = _numeric_column_arrow(values)
+        if fast is not NotImplemented:
+            return fast
+    return _numeric_column_loop(values)
+
+
+def _numeric_column_arrow(values):
+    try:
+        import pyarrow as pa
+        import pyarrow.compute as pc
+        arr = pa.array(values)
+    except Exception:                          # ArrowInvalid / ArrowTypeError / OverflowError: let the loop decide
+        return NotImplemented
+    t, n = arr.type, len(arr)
+    if pa.types.is_null(t):
+        return np.full(n, math.nan), np.zeros(n, dtype=bool), "int"
+    if pa.types.is_integer(t):
+        mm = pc.min_max(arr)
+        lo, hi = mm["min"].as_py(), mm["max"].as_py()
+        if lo is not None and (abs(lo) > _EXACT_INT or abs(hi) > _EXACT_INT):
+            return None
+        kind = "int"
+    elif pa.types.is_floating(t):
+        kind = "float"
+    else:
+        return None if (pa.types.is_string(t) or pa.types.is_boolean(t) or pa.types.is_large_string(t)) else NotImplemented
+    valid = ~np.asarray(arr.is_null().to_numpy(zero_copy_only=False), dtype=bool)
+    out = np.asarray(pc.cast(arr, pa.float64()).fill_null(math.nan).to_numpy(zero_copy_only=False), dtype=np.float64)
+    return np.ascontiguousarray(out), valid, kind
+
+
+def _numeric_column_loop(values):
     n = len(values)
     out = np.empty(n, dtype=np.float64)
     valid = np.ones(n, dtype=bool)
@@ -64,6 +100,31 @@ def group_key(value):
     if isinstance(value, str):
         return ("str", value)
     return ("other", repr(value))
+
+
+def pack_cells(cells):
+    """(chars uint8[total], offsets int64[n+1]) of a list of ``str`` / ``bytes`` cells — the layout the GPU parser and
+    the byte-wise group-by read.  Arrow does the UTF-8 encoding and the concatenation in C++."""
+    n = len(cells)
+    if n == 0:
+        return np.zeros(1, dtype=np.uint8), np.zeros(1, dtype=np.int64)
+    try:
+        import pyarrow as pa
+        is_text = isinstance(cells[0], str)
+        arr = pa.array(cells, type=pa.large_string() if is_text else pa.large_binary())
+        if arr.null_count:
+            raise ValueError("null cell")
+        bufs = arr.buffers()
+        offsets = np.frombuffer(bufs[1], dtype=np.int64, count=n + 1 + arr.offset)[arr.offset:]
+        data = np.frombuffer(bufs[2], dtype=np.uint8) if bufs[2] is not None and bufs[2].size else np.zeros(1, dtype=np.uint8)
+        if offsets[0] != 0:
+            data, offsets = data[offsets[0]:], offsets - offsets[0]
+        return np.ascontiguousarray(data) if data.size else np.zeros(1, dtype=np.uint8), np.ascontiguousarray(offsets)
+    except Exception:                          # mixed str / bytes, exotic objects: encode one by one
+        enc = [c.encode("utf-8") if isinstance(c, str) else bytes(c) for c in cells]
+        offsets = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum([len(b) for b in enc], out=offsets[1:])
+        return np.frombuffer(b"".join(enc) + b"\0", dtype=np.uint8), offsets
 
 
 def dictionary_encode(values):

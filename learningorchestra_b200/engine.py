@@ -358,12 +358,9 @@ class Engine:
     def parse_number_host(self, cells):
         """cells: list of ``str`` / ``bytes``.  Returns (values float64[n], status uint8[n]) — values are what
         CPython's ``float(cell)`` returns, status as LO_NUM_* (``_native``)."""
-        enc = [c.encode("utf-8") if isinstance(c, str) else bytes(c) for c in cells]
-        n = len(enc)
-        offsets = np.zeros(n + 1, dtype=np.int64)
-        if n:
-            np.cumsum([len(b) for b in enc], out=offsets[1:])
-        chars = np.frombuffer(b"".join(enc) + b"\0", dtype=np.uint8)
+        from .columnar import pack_cells
+        n = len(cells)
+        chars, offsets = pack_cells(cells)
         values = np.zeros(n, dtype=np.float64)
         status = np.zeros(n, dtype=np.uint8)
         N.check(self._lib.lo_parse_number_host(self._ctx, chars.ctypes.data_as(C.c_void_p), offsets.ctypes.data_as(C.c_void_p),
@@ -412,12 +409,9 @@ class Engine:
     def value_counts_str_host(self, cells):
         """cells: list of ``str`` / ``bytes``.  Returns (rep_rows int64[g], counts uint64[g]): one representative row
         per distinct cell and the group sizes (GPU hash group-by on the bytes, exact)."""
-        enc = [c.encode("utf-8") if isinstance(c, str) else bytes(c) for c in cells]
-        n = len(enc)
-        offsets = np.zeros(n + 1, dtype=np.int64)
-        if n:
-            np.cumsum([len(b) for b in enc], out=offsets[1:])
-        chars = np.frombuffer(b"".join(enc) + b"\0", dtype=np.uint8)
+        from .columnar import pack_cells
+        n = len(cells)
+        chars, offsets = pack_cells(cells)
         cap = max(min(n, 1 << 16), 1)
         while True:
             rows = np.empty(cap, dtype=np.int64)

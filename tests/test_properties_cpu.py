@@ -176,3 +176,35 @@ def test_datatype_number_equals_the_reference_loop_on_arbitrary_cells(cells, poi
         same = (g["v"] == e["v"] and type(g["v"]) is type(e["v"])) or (isinstance(g["v"], float) and g["v"] != g["v"] and e["v"] != e["v"])
         assert same, (g, e)
     assert db.find_one("t", {"_id": 0})["finished"] is (not failed)
+
+
+@settings(max_examples=300, deadline=None)
+@given(values=st.lists(st.one_of(st.none(), st.integers(-2 ** 62, 2 ** 62), st.integers(-5, 5), st.floats(allow_nan=True),
+                                 st.booleans(), st.text(max_size=2)), min_size=64, max_size=120),
+       homogeneous=st.sampled_from(["any", "ints", "floats", "text", "nulls"]))
+def test_arrow_fast_path_packs_exactly_like_the_loop(values, homogeneous):
+    if homogeneous == "ints":
+        values = [v if (v is None or (isinstance(v, int) and not isinstance(v, bool))) else 3 for v in values]
+    elif homogeneous == "floats":
+        values = [v if (v is None or isinstance(v, float)) else (1.5 if not isinstance(v, int) or isinstance(v, bool) else v % 7) for v in values]
+    elif homogeneous == "text":
+        values = [v if (v is None or isinstance(v, str)) else "x" for v in values]
+    elif homogeneous == "nulls":
+        values = [None] * len(values)
+    fast, slow = columnar.numeric_column(values), columnar._numeric_column_loop(values)
+    assert (fast is None) == (slow is None)
+    if fast is not None:
+        assert fast[2] == slow[2] and np.array_equal(fast[1], slow[1])
+        assert np.array_equal(fast[0].view(np.uint64)[fast[1]], slow[0].view(np.uint64)[slow[1]])
+        assert np.isnan(fast[0][~fast[1]]).all()
+
+
+@settings(max_examples=200, deadline=None)
+@given(cells=st.lists(st.text(max_size=6), max_size=50), as_bytes=st.booleans())
+def test_pack_cells_layout(cells, as_bytes):
+    src = [c.encode("utf-8") for c in cells] if as_bytes else cells
+    chars, offsets = columnar.pack_cells(src)
+    enc = [c.encode("utf-8") for c in cells]
+    assert offsets.dtype == np.int64 and offsets.shape == (len(cells) + 1,) and offsets[0] == 0
+    for i, b in enumerate(enc):
+        assert bytes(chars[offsets[i]:offsets[i + 1]]) == b
