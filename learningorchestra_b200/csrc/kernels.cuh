@@ -6,16 +6,23 @@
 //   histogram_image/histogram.py:31-36            per-field value counting  -> K3/K4
 //
 // Design:
-//   * table = columnar slabs in HBM; a work tile is (projected column j, kTileRows rows).
-//   * every thread streams 32-byte (LDG.E.256) vectors of its column slab with
-//     L1::no_allocate / L2::evict_first, converts, and streams the result out with st.cs.
-//   * histogram = PRIVATE PER-THREAD BYTE COUNTERS in shared memory, laid out so that
-//     thread t only ever touches bank (t % 32): word w of thread t lives at smem word
-//     w*kThreads + t.  Increment = plain LDS.U8 / IADD / STS.U8 — no atomics, no bank
-//     conflicts, and the cost is independent of the value distribution (a constant column
-//     is as fast as a uniform one).  A thread handles <= 255 elements per tile so a byte
-//     never wraps; the CTA then folds the 256 private histograms with packed 16-bit adds
-//     + warp shuffles and issues one RED.64 per non-empty bin.
+//   * table = columnar slabs in HBM; a work tile is (projected column j, kTileRows rows), one tile per CTA
+//     (the grid de-phases itself: a persistent, lockstep variant measured 20 % slower).
+//   * k_project_cast_hist: every thread streams 32-byte (LDG.E.256) vectors of its column slab with
+//     L1::no_allocate / L2::evict_first through a 2 x 5-vector register pipeline, converts, and streams the
+//     result out with st.cs.  k_project_cast_hist_tma is the same tile fed by cp.async.bulk + mbarriers
+//     (opt-in; measured equal).
+//   * histogram = PRIVATE PER-THREAD BYTE COUNTERS in shared memory, laid out so that thread t only ever
+//     touches bank (t % 32): word w of thread t lives at smem word w*kThreads + t.  Increment = plain
+//     LDS.U8 / IADD / STS.U8 (f64 kernel) or one ATOMS.ADD on the containing word (byte kernel) — no bank
+//     conflicts, and the cost is independent of the value distribution (a constant column is as fast as a
+//     uniform one).  A thread handles <= 255 elements per tile so a byte never wraps; the CTA then folds the 256
+//     private histograms with packed 16-bit adds + warp shuffles and issues one RED.64 per non-empty bin
+//     (system scope when the count matrix lives in a peer GPU's memory: the multi-GPU merge rides on the flush).
+//   * bin index = trunc(RN((x - lo) / w)) computed without a divide (hoisted reciprocal + two FMA
+//     corrections, proven and exhaustively self-tested equal to the IEEE quotient; bin_index_f32).
+//   * also here: k_parse_number (CPython float() on the GPU, parse_number.cuh), k_hash_count_f64 / _str
+//     (exact group-by), k_minmax_cast, the peer-merge flag kernels, generators, checksum.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
