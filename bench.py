@@ -36,7 +36,11 @@ sys.path.insert(0, str(ROOT))
 SEED = 20260921
 GEN_LO, GEN_HI = -1000.0, 1000.0
 NBINS = 256
-METRIC = "rows/sec project+cast+histogram 100M x 32 fp64->fp32"
+METRIC = "rows/sec project+cast+histogram 100M\u00d732 fp64\u2192fp32; HBM GB/s vs peak @1/2/4/8 GPU"   # BASELINE.json "metric"
+try:
+    METRIC = json.loads((ROOT / "BASELINE.json").read_text())["metric"]
+except Exception:
+    pass
 
 
 def log(*a):
