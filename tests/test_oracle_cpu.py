@@ -118,3 +118,17 @@ def test_linearity_of_counts():
     whole = cport.hist_f32(x, -1000, 1000, 256)
     parts = sum(cport.hist_f32(x[a:b], -1000, 1000, 256) for a, b in [(0, 1), (1, 33333), (33333, 100000)])
     np.testing.assert_array_equal(whole, parts)
+
+
+def test_cast_has_a_third_independent_witness():
+    """fp64 -> fp32 RNE as computed by torch's CPU kernels (another code base, another compiler) agrees bit for bit
+    with both oracle restatements on the generator's special values and on random doubles (NaNs canonicalised)."""
+    import torch
+    rng = np.random.default_rng(17)
+    x = np.concatenate([bn.special_values(-1000.0, 1000.0), rng.standard_normal(50_000) * 10.0 ** rng.integers(-45, 40, 50_000),
+                        rng.integers(0, 2 ** 63, 50_000, dtype=np.uint64).view(np.float64)])
+    t = torch.from_numpy(x.copy()).to(torch.float32).numpy()
+    tb = t.view(np.uint32).copy()
+    tb[np.isnan(t)] = 0x7FC00000
+    np.testing.assert_array_equal(tb, _bits(bn.cast_f64_f32(x)))
+    np.testing.assert_array_equal(tb, _bits(cport.cast_f64_f32(x)))
