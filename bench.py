@@ -203,7 +203,22 @@ def run_reference_arm(args) -> None:
 # ======================================================================================================
 # GPU arm
 # ======================================================================================================
+def _claim_stdout() -> int:
+    """The contract is ONE JSON line on stdout.  Libraries talk on fd 1 too (NCCL prints its version banner there
+    when NCCL_DEBUG=VERSION is in the environment), so fd 1 is pointed at stderr for the whole run and the JSON line
+    is written to a private duplicate of the real stdout at the end."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return real
+
+
+def _emit(real_stdout: int, line: dict) -> None:
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
+
+
 def run_gpu(args) -> None:
+    real_stdout = _claim_stdout()
     import torch
     import torch.distributed as dist
 
@@ -432,7 +447,7 @@ def run_gpu(args) -> None:
                 line["roofline"]["traffic_source"] = "ncu --set full dram__bytes_read+write of one 100M x 32 launch (profiles/), scaled to this launch's rows"
             except Exception:
                 pass
-        print(json.dumps(line), flush=True)
+        _emit(real_stdout, line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
