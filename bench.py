@@ -1,20 +1,26 @@
 #!/usr/bin/env python
-"""bench.py — rows/s of the fused projection + fp64->fp32 cast + 256-bin histogram hot path.
+"""bench.py — rows/s of the projection -> fp64->fp32 cast -> histogram hot path on B200.
 
-Workload (BASELINE.json configs[2]/[3], SURVEY.md §8d "S100"): synthetic columnar table,
-100 000 000 rows x 32 fp64 columns, K = 32 projected columns (a fixed permutation), fp32 output
-table written, 256-bin histogram of every projected column over [-1000, 1000].  With N GPUs the
-rows are range-sharded (rank r owns rows [r*R/N, (r+1)*R/N)) and the per-GPU partial histograms
-are merged by ONE NCCL all-reduce per step (strong scaling: the table size is fixed).
+Workloads (BASELINE.json ``configs``):
 
-One "step" = one pass of the hot path over the (rank's shard of the) table:
-    zero counts -> fused kernel -> (N > 1) all-reduce of the uint64 count matrix.
+* ``s100`` (default; configs[2] at N = 1, configs[3] at N > 1): synthetic columnar table, 100 000 000 rows x 32 fp64
+  columns, K = 32 projected columns (a fixed permutation), fp32 output table written, 256-bin histogram of every
+  projected column over [-1000, 1000].
+* ``s10`` (configs[1]): 10 000 000 x 16 fp64, projection + fp32 cast only.
+* ``m`` (configs[4]): MNIST-shaped 1 000 000 x 784 uint8 table, per-column 256-bin value counts.
 
-Output: ONE JSON line on rank 0 (see README / DESIGN.md §6 for the keys).
+With N GPUs (one rank per GPU, torchrun) the rows are range-sharded and every step's partial histograms are merged
+by the library itself (``ShardedEngine`` -> ``lo_group_*``): in-kernel peer-memory merge over NVLink, or one NCCL
+all-reduce (``--merge nccl``).  Strong scaling: the table size is fixed.  One "step" = one pass of the hot path over
+the table, merge included.  After the timed region the merged counts and the fp32 output checksums of EVERY run are
+compared with oracle-made goldens (tests/golden/bench_goldens.json); a mismatch fails the run (rc 3).
 
-    python bench.py                       # 1 GPU, defaults
-    torchrun ... bench.py --gpus 8        # one rank per GPU
-    python bench.py --impl reference      # CPU arm: the oracle port on all host cores
+Output: ONE JSON line on rank 0.
+
+    python bench.py                            # 1 GPU, s100
+    python bench.py --workload m               # config M
+    torchrun ... bench.py --gpus 8             # one rank per GPU
+    python bench.py --impl reference           # CPU arm: the oracle port on all host cores
 """
 from __future__ import annotations
 
@@ -36,11 +42,21 @@ sys.path.insert(0, str(ROOT))
 SEED = 20260921
 GEN_LO, GEN_HI = -1000.0, 1000.0
 NBINS = 256
-METRIC = "rows/sec project+cast+histogram 100M\u00d732 fp64\u2192fp32; HBM GB/s vs peak @1/2/4/8 GPU"   # BASELINE.json "metric"
+GOLDENS = ROOT / "tests" / "golden" / "bench_goldens.json"
+METRIC = "rows/sec project+cast+histogram 100M×32 fp64→fp32; HBM GB/s vs peak @1/2/4/8 GPU"   # BASELINE.json "metric"
 try:
     METRIC = json.loads((ROOT / "BASELINE.json").read_text())["metric"]
 except Exception:
     pass
+
+WORKLOADS = {
+    # name: (rows, cols, dtype label, algorithmic bytes per row per projected column)
+    "s100": {"rows": 100_000_000, "cols": 32, "dtype": "f64->f32", "bytes_per_elem": 12.0,
+             "kernel": "lo::k_project_cast_hist<1,true,true,true>"},
+    "s10": {"rows": 10_000_000, "cols": 16, "dtype": "f64->f32", "bytes_per_elem": 12.0,
+            "kernel": "lo::k_project_cast_hist<1,false,true,false>"},
+    "m": {"rows": 1_000_000, "cols": 784, "dtype": "u8", "bytes_per_elem": 1.0, "kernel": "lo::k_hist_u8_cols<true>"},
+}
 
 
 def log(*a):
@@ -52,6 +68,10 @@ def projected_columns(ncols: int) -> list[int]:
     return [(7 * j + 3) % ncols for j in range(ncols)] if ncols % 7 else list(range(ncols))[::-1]
 
 
+def workload_columns(workload: str, ncols: int) -> list[int]:
+    return list(range(ncols)) if workload == "m" else projected_columns(ncols)
+
+
 def peaks() -> tuple[float, str]:
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -60,6 +80,15 @@ def peaks() -> tuple[float, str]:
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def workload_text(workload: str, rows: int, ncols: int, k: int) -> str:
+    if workload == "m":
+        return f"per-column 256-bin value counts, {rows} x {ncols} uint8 (MNIST-shaped), columnar"
+    if workload == "s10":
+        return f"projection + fp32 cast, {rows} x {ncols} fp64 -> fp32, K={k} (permutation), columnar"
+    return (f"fused project+cast+{NBINS}-bin histogram, {rows} x {ncols} fp64 -> fp32, K={k} (permutation), columnar, "
+            f"range [{GEN_LO}, {GEN_HI}]")
 
 
 class ClockSampler:
@@ -131,68 +160,113 @@ class ClockSampler:
 
 
 # ======================================================================================================
-# CPU arm: the oracle port (oracle/bsem.c, OpenMP, all host cores) on a bounded sample of the workload
+# CPU arm: the oracle port (oracle/bsem.c, OpenMP, all host cores)
 # ======================================================================================================
-def cpu_pass_setup(sample_rows: int, ncols: int):
+def _cpu_sample_rows(workload: str, rows: int, ncols: int, requested: int) -> int:
+    """Rows of the CPU sample: the WHOLE table when the host has the memory for it (so the arm runs the same
+    config), else a bounded prefix; ``--cpu-rows`` forces a size."""
+    if requested:
+        return min(rows, requested)
+    import psutil
+    per_row = ncols * (1 if workload == "m" else 12)
+    fit = int(psutil.virtual_memory().available * 0.5 / per_row)
+    return rows if fit >= rows else max(1_000_000, fit // 1_000_000 * 1_000_000)
+
+
+def cpu_pass_setup(workload: str, sample_rows: int, ncols: int):
+    """Builds the oracle, generates the sample with the same OpenMP team / static row partition that later scans it
+    (parallel first touch: every page lives on the NUMA node of the thread that reads it), returns one_pass()."""
+    os.environ.setdefault("OMP_PROC_BIND", "close")
+    os.environ.setdefault("OMP_PLACES", "cores")
     from learningorchestra_b200.build import build_oracle
     build_oracle()
-    from oracle import cport
-    cport.use_all_cores()
-    cols = [cport.synth_f64(0, SEED, c, 0, sample_rows, GEN_LO, GEN_HI) for c in range(ncols)]
-    proj = [cols[c] for c in projected_columns(ncols)]
-    lo = np.full(ncols, GEN_LO, np.float32)
-    hi = np.full(ncols, GEN_HI, np.float32)
-    outs = [np.empty(sample_rows, dtype=np.float32) for _ in range(ncols)]
-
     import ctypes as C
+    from oracle import cport
+    threads = cport.use_all_cores()
     L = cport.lib()
-    in_p = (C.POINTER(C.c_double) * ncols)(*[a.ctypes.data_as(C.POINTER(C.c_double)) for a in proj])
-    out_p = (C.POINTER(C.c_float) * ncols)(*[a.ctypes.data_as(C.POINTER(C.c_float)) for a in outs])
-    counts = np.zeros((ncols, NBINS), dtype=np.uint64)
+    cols = workload_columns(workload, ncols)
+    k = len(cols)
+    idx = np.ascontiguousarray(cols, dtype=np.int32)
+    if workload == "m":
+        ins = [np.empty(sample_rows, dtype=np.uint8) for _ in range(k)]
+        in_p = (C.c_void_p * k)(*[a.ctypes.data for a in ins])
+        L.oracle_synth_fill_u8_mt(C.c_uint64(SEED), idx.ctypes.data_as(C.c_void_p), C.c_int(k), C.c_int64(0),
+                                  C.c_int64(sample_rows), in_p)
+        counts = np.zeros((k, 256), dtype=np.uint64)
+
+        def one_pass():
+            L.oracle_hist_u8_cols(in_p, C.c_int64(sample_rows), C.c_int(k), counts.ctypes.data_as(C.c_void_p))
+            return counts
+        return one_pass, threads, (ins,)
+    ins = [np.empty(sample_rows, dtype=np.float64) for _ in range(k)]
+    outs = [np.empty(sample_rows, dtype=np.float32) for _ in range(k)]
+    in_p = (C.c_void_p * k)(*[a.ctypes.data for a in ins])
+    out_p = (C.c_void_p * k)(*[a.ctypes.data for a in outs])
+    L.oracle_synth_fill_f64_mt(C.c_int(0), C.c_uint64(SEED), idx.ctypes.data_as(C.c_void_p), C.c_int(k), C.c_int64(0),
+                               C.c_int64(sample_rows), C.c_double(GEN_LO), C.c_double(GEN_HI), in_p, out_p)
+    nb = NBINS if workload == "s100" else 0
+    lo = np.full(k, GEN_LO, np.float32)
+    hi = np.full(k, GEN_HI, np.float32)
+    counts = np.zeros((k, max(nb, 1)), dtype=np.uint64)
 
     def one_pass():
-        L.oracle_project_cast_hist(in_p, C.c_int64(sample_rows), C.c_int(ncols), out_p, C.c_int(NBINS),
+        L.oracle_project_cast_hist(in_p, C.c_int64(sample_rows), C.c_int(k), out_p, C.c_int(nb),
                                    lo.ctypes.data_as(C.c_void_p), hi.ctypes.data_as(C.c_void_p),
                                    counts.ctypes.data_as(C.c_void_p))
         return counts
+    return one_pass, threads, (ins, outs)
 
-    return one_pass, cport.num_threads(), (proj, outs)
+
+def _sample_text(workload, sample_rows, rows, ncols, threads):
+    whole = "the whole table" if sample_rows == rows else f"the first {sample_rows} rows of the {rows}-row table"
+    return (f"{whole} x {ncols} cols of the same synthetic data, host-resident columns generated and scanned by the "
+            f"same {threads}-thread OpenMP team (static row partition, parallel first touch, OMP_PROC_BIND=close), "
+            "oracle port oracle/bsem.c (gcc -O2 -fopenmp); the reference's own PySpark+MongoDB path cannot run here "
+            "(no JVM / pyspark / pymongo / mongod)")
 
 
-def run_cpu_baseline(ncols: int, sample_rows: int, passes: int = 3) -> dict:
-    one_pass, threads, _keep = cpu_pass_setup(sample_rows, ncols)
+def run_cpu_baseline(workload: str, rows: int, ncols: int, requested_rows: int, budget_s: float = 25.0) -> dict:
+    sample_rows = _cpu_sample_rows(workload, rows, ncols, requested_rows)
+    one_pass, threads, _keep = cpu_pass_setup(workload, sample_rows, ncols)
     one_pass()
-    best = float("inf")
-    for _ in range(passes):
+    times, t_all = [], time.perf_counter()
+    while len(times) < 7 and (len(times) < 3 or time.perf_counter() - t_all < budget_s):
         t0 = time.perf_counter()
         one_pass()
-        best = min(best, time.perf_counter() - t0)
-    return {"value": sample_rows / best, "unit": "rows/s", "cores": threads, "kind": "port",
-            "sample": f"{sample_rows} rows x {ncols} cols of the same synthetic table, host-resident, "
-                      f"oracle/bsem.c (gcc -O2 -fopenmp), best of {passes} passes; the reference's own "
-                      "PySpark+MongoDB path cannot run here (no JVM/pyspark/pymongo/mongod)"}
+        times.append(time.perf_counter() - t0)
+    med = statistics.median(times)
+    return {"value": sample_rows / med, "unit": "rows/s", "cores": threads, "kind": "port", "passes": len(times),
+            "sample_rows": sample_rows, "same_config": sample_rows == rows,
+            "sample": _sample_text(workload, sample_rows, rows, ncols, threads) + f"; median of {len(times)} passes"}
 
 
 def run_reference_arm(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    ncols, sample_rows = args.cols, args.cpu_rows
-    one_pass, threads, _keep = cpu_pass_setup(sample_rows, ncols)
+    w = args.workload
+    ncols, rows = args.cols, args.rows
+    sample_rows = _cpu_sample_rows(w, rows, ncols, args.cpu_rows)
+    one_pass, threads, _keep = cpu_pass_setup(w, sample_rows, ncols)
     for _ in range(args.warmup):
         one_pass()
-    t0 = time.perf_counter()
+    times = []
     for _ in range(args.steps):
+        t0 = time.perf_counter()
         one_pass()
-    dt = time.perf_counter() - t0
+        times.append(time.perf_counter() - t0)
+    dt = sum(times)
     value = sample_rows * args.steps / dt
-    sample = (f"each step = {sample_rows} rows x {ncols} cols (bounded sample of the {args.rows}-row table), "
-              "host-resident columns, oracle port oracle/bsem.c with OpenMP on all host cores")
+    k = len(workload_columns(w, ncols))
+    sample = _sample_text(w, sample_rows, rows, ncols, threads)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f64->f32", "data": "synthetic",
-        "config": {"workload": f"fused project+cast+{NBINS}-bin histogram, {args.rows} x {ncols} fp64 -> fp32, K={ncols}",
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "ms_per_step_median": statistics.median(times) * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": WORKLOADS[w]["dtype"], "data": "synthetic",
+        "config": {"workload": workload_text(w, rows, ncols, k), "name": w, "rows": rows, "cols": ncols, "k": k,
+                   "nbins": NBINS if w != "s10" else 0, "sample_rows": sample_rows, "threads": threads,
+                   "same_config": sample_rows == rows,
                    "note": "reference PySpark/MongoDB stack is not runnable offline; this is the CPU oracle port"},
         "cpu_baseline": {"value": value, "unit": "rows/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -217,13 +291,25 @@ def _emit(real_stdout: int, line: dict) -> None:
     os.write(real_stdout, (json.dumps(line) + "\n").encode())
 
 
-def run_gpu(args) -> None:
+def load_goldens(workload: str, rows: int, ncols: int):
+    try:
+        g = json.loads(GOLDENS.read_text())[workload]
+    except Exception:
+        return None
+    if g["rows"] != rows or g["cols"] != ncols or g["seed"] != SEED:
+        return None
+    return g
+
+
+def run_gpu(args) -> int:
     real_stdout = _claim_stdout()
     import torch
     import torch.distributed as dist
 
+    from learningorchestra_b200 import _native as N
     from learningorchestra_b200.build import build_native
     from learningorchestra_b200.engine import Engine
+    from learningorchestra_b200.sharding import ShardedEngine
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -240,68 +326,47 @@ def run_gpu(args) -> None:
     if world > 1:
         dist.barrier()                      # nobody loads libloexec.so while rank 0 might be rewriting it
 
+    w = args.workload
     eng = Engine(local_rank)
+    if world > 1:
+        sh = ShardedEngine.from_torch_distributed(eng, merge={"p2p": "peer"}.get(args.merge, args.merge))
+    else:
+        sh = ShardedEngine.from_exchange(eng, 0, 1, lambda b: [b], lambda ok: ok, merge="peer")
     ncols, total_rows = args.cols, args.rows
-    from learningorchestra_b200.sharding import allreduce_counts, shard_bounds
-    r_begin, r_end = shard_bounds(total_rows, world, rank)
-    nrows = r_end - r_begin
-    cols = projected_columns(ncols)
+    cols = workload_columns(w, ncols)
     k = len(cols)
-    # a non-default stream: libloexec launches on exactly the stream it is handed (NULL would mean its
-    # own), and torch.cuda.Event / NCCL then see the same stream
+    # a non-default stream: libloexec launches on exactly the stream it is handed (NULL would mean its own), and
+    # torch.cuda.Event then sees the same stream
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
+    streams = [stream]
 
-    table = eng.table("f64", nrows, ncols).fill_synthetic(0, SEED, row_offset=r_begin, lo=GEN_LO, hi=GEN_HI, stream=stream)
-    out = eng.table("f32", nrows, k)
-    counts_t = torch.zeros(k * NBINS, dtype=torch.int64, device="cuda")      # uint64 bit patterns; sums are identical
-    counts = eng.wrap_counts(k, NBINS, counts_t.data_ptr(), keepalive=counts_t)
     lo = np.full(k, GEN_LO, np.float32)
     hi = np.full(k, GEN_HI, np.float32)
+    if w == "m":
+        table = sh.table("u8", total_rows, ncols).fill_synthetic(N.LO_SYNTH_MNIST_U8, SEED, streams=streams)
+        out = None
+    else:
+        table = sh.table("f64", total_rows, ncols).fill_synthetic(N.LO_SYNTH_UNIFORM, SEED, lo=GEN_LO, hi=GEN_HI, streams=streams)
+        out = sh.table("f32", total_rows, k)
+    nrows = table.local_rows
     torch.cuda.synchronize()
 
-    # N > 1: "p2p" fuses the merge into the kernel's flush (system-scope REDs into rank 0's matrix over NVLink);
-    # "nccl" is local counts + one all-reduce.  "auto" = p2p when the CUDA-IPC setup succeeds on every rank and a
-    # probe step completes without a flag time-out, else nccl — both are GPU paths, the line says which ran.
-    peer, merge_note = None, "nccl"
-    if world > 1 and args.merge in ("p2p", "auto"):
-        from learningorchestra_b200.sharding import PeerReduce
-        ok = torch.ones(1, device="cuda")
-        try:
-            peer = PeerReduce(eng, k, NBINS)
-        except Exception as exc:          # e.g. IPC not permitted in this container
-            log(f"[rank {rank}] peer-memory merge unavailable: {exc!r}")
-            ok.zero_()
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        if float(ok[0]) == 0.0:
-            if args.merge == "p2p":
-                raise SystemExit("--merge p2p requested but the peer-memory setup failed")
-            if peer is not None:
-                peer.close()
-            peer = None
-        merge_note = "p2p" if peer is not None else "nccl (p2p setup failed)"
-
-    kev = []   # (start, end) events around the fused kernel only, for the roofline
+    kev = []   # (start, end) events around the library call of one step, for the roofline
 
     def step(record: bool):
-        if peer is not None:
-            # merge fused into the kernel's flush: system-scope REDs into the root's matrix over NVLink
-            peer.before_kernel(stream)
-            dst, is_peer = peer.counts_for_step(), True
-        else:
-            counts.zero(stream)
-            dst, is_peer = counts, False
         if record:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-        eng.project_cast_hist(table, cols, NBINS, lo, hi, out=out, counts=dst, stream=stream, peer_counts=is_peer)
+        if w == "s100":
+            sh.project_cast_hist(table, cols, NBINS, lo, hi, out=out, streams=streams)
+        elif w == "s10":
+            sh.project_cast(table, cols, out=out, streams=streams)
+        else:
+            sh.hist_u8_cols(table, cols, streams=streams)
         if record:
             e1.record(stream)
             kev.append((e0, e1))
-        if peer is not None:
-            peer.after_kernel(stream)
-        elif world > 1:
-            allreduce_counts(counts_t)          # ONE ncclAllReduce of k*nbins int64 over NVLink, same stream
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -309,24 +374,17 @@ def run_gpu(args) -> None:
     for _ in range(args.warmup):
         step(False)
     torch.cuda.synchronize()
-    if peer is not None:
-        bad = torch.tensor([float(peer.timed_out(stream))], device="cuda")
-        dist.all_reduce(bad, op=dist.ReduceOp.MAX)
-        if float(bad[0]) > 0:
-            if args.merge == "p2p":
-                raise SystemExit("peer-memory merge timed out during warm-up")
-            log(f"[rank {rank}] peer-memory merge timed out in warm-up; using the NCCL all-reduce")
-            peer.close()
-            peer, merge_note = None, "nccl (p2p timed out in warm-up)"
-            for _ in range(args.warmup):
-                step(False)
-            torch.cuda.synchronize()
+    if sh.timeouts():
+        raise SystemExit("a device-side wait of the merge timed out during warm-up")
     sampler.wait_ready()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     sampler.mark_start()
     launches0 = eng.launch_count
+    # all GPUs enter the timed region together: a device-side barrier on the timing stream (a host barrier
+    # leaves tens of microseconds of skew, which the root would then spend waiting inside step 0's merge)
+    sh.barrier(streams)
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_start.record(stream)
     for _ in range(args.steps):
@@ -334,35 +392,57 @@ def run_gpu(args) -> None:
     t_end.record(stream)
     torch.cuda.synchronize()
     sampler.mark_end()
+    launches = eng.launch_count - launches0 - 1          # the barrier launch is outside the timed region
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
-    launches = eng.launch_count - launches0
     elapsed_ms = t_start.elapsed_time(t_end)
     kernel_ms = [a.elapsed_time(b) for a, b in kev]
     t = torch.tensor([elapsed_ms, sum(kernel_ms) / len(kernel_ms)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     elapsed_ms, kernel_ms_avg = float(t[0]), float(t[1])
-    if peer is not None:
-        assert peer.timed_out(stream) == 0, "peer-memory merge timed out"
-        final_counts = peer.result_numpy(stream)
-    else:
-        final_counts = counts.to_numpy(stream)
-    if final_counts is not None:
-        total_counted = int(final_counts.sum())
-        assert total_counted == total_rows * k, f"histogram lost rows: {total_counted} != {total_rows * k}"
+    assert sh.timeouts() == 0, "a device-side wait of the merge timed out"
 
-    # ---- end to end: host buffers in, host buffers out, through the plugin-facing C-ABI call ----------
-    e2e = None
-    e2e_ready = False
+    # ---- parity of THIS run against the oracle-made goldens (every N, every workload) ---------------------
+    gold = load_goldens(w, total_rows, ncols)
+    parity = {"golden": str(GOLDENS.relative_to(ROOT)) if gold else None}
+    final_counts = None
+    if w != "s10" and sh.has_result:
+        final_counts = sh.result(k * NBINS).reshape(k, NBINS)
+    if out is not None:
+        def as_i64(u: int) -> int:
+            return u - (1 << 64) if u >= (1 << 63) else u
+        sums = torch.tensor([as_i64(out.checksum(j)) for j in range(k)], dtype=torch.int64, device="cuda")
+        if world > 1:
+            dist.all_reduce(sums)                     # two's-complement wrap == addition mod 2^64
+        sums = [int(v) & 0xFFFFFFFFFFFFFFFF for v in sums.cpu().tolist()]
+    if rank == 0:
+        if final_counts is not None:
+            total_counted = int(final_counts.sum())
+            assert total_counted == total_rows * k, f"histogram lost rows: {total_counted} != {total_rows * k}"
+        if gold is None:
+            parity["note"] = "no golden for this rows / cols / seed; only the row-conservation check ran"
+        else:
+            if final_counts is not None:
+                parity["counts"] = bool(np.array_equal(final_counts, np.array(gold["counts"], dtype=np.uint64).reshape(k, NBINS)))
+            if out is not None:
+                parity["checksums"] = sums == [int(x) for x in gold["checksums"]]
+        parity["ok"] = all(v for kk, v in parity.items() if kk in ("counts", "checksums"))
+
+    # ---- end to end: host buffers in, host buffers out, through the same group API ------------------------
+    e2e, e2e_ready = None, False
     if not args.no_e2e:
-        import ctypes as C
         import psutil
-        from learningorchestra_b200 import _native as N
+        saved_affinity = os.sched_getaffinity(0)
+        numa = None
+        try:
+            numa = eng.bind_numa()             # pinned buffers below are first touched next to this rank's GPU
+        except Exception as exc:               # noqa: BLE001
+            log(f"[rank {rank}] NUMA binding unavailable: {exc!r}")
         avail = psutil.virtual_memory().available
-        per_row = 12 * k
+        per_row = (1 if w == "m" else 12) * k
         budget_rows = int(avail * 0.45 / world / per_row)
         e2e_rows = min(nrows, args.e2e_rows if args.e2e_rows else nrows, budget_rows)
         e2e_rows = max(61440, e2e_rows // 61440 * 61440) if e2e_rows >= 61440 else e2e_rows
@@ -370,13 +450,20 @@ def run_gpu(args) -> None:
         # is skipped on ALL ranks together rather than leaving some of them waiting in a collective
         setup_error = None
         try:
-            hin = eng.pinned_empty((k, e2e_rows), np.float64)
-            hout = eng.pinned_empty((k, e2e_rows), np.float32)
+            hin = eng.pinned_empty((k, e2e_rows), np.uint8 if w == "m" else np.float64)
+            hout = eng.pinned_empty((k, e2e_rows), np.float32) if w != "m" else None
             for j in range(k):   # host inputs = the projected columns of this rank's shard (device -> pinned host, untimed)
-                N.check(eng._lib.lo_table_download_col(eng._ctx, table._h, cols[j], 0, hin[j].ctypes.data_as(C.c_void_p), e2e_rows))
+                table.shards[0].to_numpy(cols[j], 0, e2e_rows, out=hin[j])
             in_cols = [hin[j] for j in range(k)]
-            out_cols = [hout[j] for j in range(k)]
-            eng.project_cast_hist_host(in_cols, NBINS, lo, hi, out=out_cols)      # warm-up (allocates staging)
+            out_cols = [hout[j] for j in range(k)] if hout is not None else None
+
+            def e2e_step():
+                if w == "s100":
+                    return sh.project_cast_hist_host(in_cols, NBINS, lo, hi, out=out_cols)
+                if w == "s10":
+                    return sh.project_cast_hist_host(in_cols, None, out=out_cols)
+                return sh.hist_u8_cols_host(in_cols)
+            e2e_step()                       # warm-up (allocates staging)
         except Exception as exc:          # noqa: BLE001
             setup_error = repr(exc)
             log(f"[rank {rank}] e2e set-up failed: {setup_error}")
@@ -394,88 +481,115 @@ def run_gpu(args) -> None:
         l0 = eng.launch_count
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            c_host, tm = eng.project_cast_hist_host(in_cols, NBINS, lo, hi, out=out_cols)
-            if world > 1:
-                ct = torch.from_numpy(c_host.view(np.int64)).cuda()
-                dist.all_reduce(ct)
-                c_host = ct.cpu().numpy()
+            c_host, tm = e2e_step()
         dt = time.perf_counter() - t0
         e2e_launches = eng.launch_count - l0
         tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
-        rr = torch.tensor([e2e_rows], dtype=torch.float64, device="cuda")
+        rr = torch.tensor([float(e2e_rows), tm["h2d_bytes"], tm["d2h_bytes"]], dtype=torch.float64, device="cuda")
+        mn = torch.tensor([tm["h2d_bytes"] / dt * e2e_steps / 1e9], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             dist.all_reduce(rr, op=dist.ReduceOp.SUM)
+            dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+        e2e_parity = None
+        if rank == 0 and gold is not None and w != "s10" and int(float(rr[0])) == total_rows:
+            e2e_parity = bool(np.array_equal(c_host, np.array(gold["counts"], dtype=np.uint64).reshape(k, NBINS)))
         e2e = {"value": float(rr[0]) * e2e_steps / float(tt[0]), "unit": "rows/s",
-               "h2d_bytes_per_step": int(tm["h2d_bytes"]) * world, "d2h_bytes_per_step": int(tm["d2h_bytes"]) * world,
+               "h2d_bytes_per_step": int(float(rr[1])), "d2h_bytes_per_step": int(float(rr[2])),
                "rows_per_step": int(float(rr[0])), "steps": e2e_steps, "launches": e2e_launches,
-               "api": "Engine.project_cast_hist_host -> lo_project_cast_hist_host (pinned host buffers, "
-                      "chunked H2D / kernel / D2H on three streams)"}
+               "h2d_GBs_slowest_rank": float(mn[0]), "numa": {"node": numa[0], "cpus": numa[1]} if numa else None,
+               "counts_match_golden": e2e_parity,
+               "api": "ShardedEngine.project_cast_hist_host -> lo_group_project_cast_hist_host (pinned host buffers, "
+                      "chunked H2D / kernel / D2H on three streams per GPU, counts merged over the group)"}
+        os.sched_setaffinity(0, saved_affinity)
 
+    rc = 0
     if rank == 0:
         peak, peak_src = peaks()
-        alg_bytes = 12.0 * k * nrows                       # 8 B read + 4 B written per projected element
+        W = WORKLOADS[w]
+        alg_bytes = W["bytes_per_elem"] * k * nrows
         achieved = alg_bytes / (kernel_ms_avg * 1e-3) / 1e9
-        cpu = run_cpu_baseline(ncols, args.cpu_rows) if world == 1 and not args.no_cpu else None
+        cpu = run_cpu_baseline(w, total_rows, ncols, args.cpu_rows) if world == 1 and not args.no_cpu else None
+        gb_in = nrows * k * (1 if w == "m" else 8) / 1e9
         line = {
             "metric": METRIC, "value": total_rows * args.steps / (elapsed_ms * 1e-3), "unit": "rows/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64->f32",
+            "us_per_step": elapsed_ms / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": W["dtype"],
             "data": "synthetic",
-            "config": {"workload": f"fused project+cast+{NBINS}-bin histogram, {total_rows} x {ncols} fp64 -> fp32, "
-                                   f"K={k} (permutation), columnar, range [{GEN_LO}, {GEN_HI}]",
-                       "rows": total_rows, "cols": ncols, "k": k, "nbins": NBINS, "rows_per_gpu": nrows,
-                       "merge": merge_note if world > 1 else None,
+            "config": {"workload": workload_text(w, total_rows, ncols, k), "name": w,
+                       "rows": total_rows, "cols": ncols, "k": k, "nbins": NBINS if w != "s10" else 0, "rows_per_gpu": nrows,
+                       "merge": sh.merge if world > 1 else None,
                        "parallelism": (f"row-range shards x{world}, " + (
-                           f"one NCCL all-reduce of {k}x{NBINS} uint64 per step" if peer is None else
-                           "merge fused into the kernel flush: system-scope RED.64 into rank 0's matrix over NVLink (CUDA IPC)"))
+                           f"one NCCL all-reduce of {k}x{NBINS} uint64 per step (inside libloexec)" if sh.merge == "nccl" else
+                           "merge inside the streaming kernel: column-last CTAs push with system-scope RED.64 into rank 0's "
+                           "matrix over NVLink (CUDA IPC), arrival + root epilogue in-kernel, one launch per step"))
                                       if world > 1 else "single GPU",
-                       "l2": f"inputs larger than L2: {nrows * ncols * 8 / 1e9:.1f} GB read + "
-                             f"{nrows * k * 4 / 1e9:.1f} GB written per GPU per step (L2 = 126 MB), no flush needed"},
+                       "l2": (f"inputs larger than L2: {gb_in:.2f} GB read per GPU per step (L2 = 126 MB), no flush needed"
+                              if gb_in > 0.5 else
+                              f"{gb_in * 1e3:.0f} MB read per GPU per step: NOT larger than L2 (126 MB) at this N; "
+                              "latency-dominated, reported in microseconds")},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "lo::k_project_cast_hist<1,true,true>",
-                         "kernel_ms_avg": kernel_ms_avg, "algorithmic_bytes_per_launch": alg_bytes},
-            "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+                         "traffic": None, "peak_source": peak_src, "kernel": W["kernel"],
+                         "kernel_ms_avg": kernel_ms_avg, "algorithmic_bytes_per_launch": alg_bytes,
+                         "overhead_us_per_step": (elapsed_ms / args.steps - kernel_ms_avg) * 1e3},
+            "parity": parity, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         }
         if cpu:
             line["cpu_baseline"] = cpu
         tr = ROOT / "profiles" / "traffic.json"
         if tr.exists():
             try:
-                t100 = json.loads(tr.read_text()).get("k_project_cast_hist_bytes_per_launch")   # ncu, 100M-row launch
-                line["roofline"]["traffic"] = t100 * nrows / 100_000_000 if t100 else None
-                line["roofline"]["traffic_source"] = "ncu --set full dram__bytes_read+write of one 100M x 32 launch (profiles/), scaled to this launch's rows"
+                key = {"s100": "k_project_cast_hist_bytes_per_launch", "m": "k_hist_u8_cols_bytes_per_launch"}.get(w)
+                full = json.loads(tr.read_text()).get(key) if key else None      # ncu, one full-size launch
+                line["roofline"]["traffic"] = full * nrows / W["rows"] if full else None
+                line["roofline"]["traffic_source"] = ("ncu --set full dram__bytes_read+write of one full-size launch "
+                                                      "(profiles/), scaled to this launch's rows")
             except Exception:
                 pass
         _emit(real_stdout, line)
+        if parity.get("ok") is False or (e2e and e2e.get("counts_match_golden") is False):
+            log("PARITY FAILURE:", json.dumps(parity), json.dumps(e2e))
+            rc = 3
     if world > 1:
+        flag = torch.tensor([float(rc)], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        rc = int(flag[0])
         dist.barrier()
-        dist.destroy_process_group()
+    sh.close()
     eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return rc
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--rows", type=int, default=100_000_000)
-    ap.add_argument("--cols", type=int, default=32)
-    ap.add_argument("--cpu-rows", type=int, default=8_000_000, help="rows of the bounded CPU sample")
+    ap.add_argument("--workload", default="s100", choices=sorted(WORKLOADS))
+    ap.add_argument("--rows", type=int, default=0)
+    ap.add_argument("--cols", type=int, default=0)
+    ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the CPU sample (0 = whole table when RAM allows)")
     ap.add_argument("--e2e-rows", type=int, default=0, help="cap on e2e rows per rank (0 = whole shard if RAM allows)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--merge", default="auto", choices=["auto", "nccl", "p2p"],
-                    help="N > 1: how partial histograms are merged (NCCL all-reduce, or fused peer-memory REDs)")
+    ap.add_argument("--merge", default="auto", choices=["auto", "nccl", "p2p", "peer"],
+                    help="N > 1: how partial histograms are merged (in-kernel peer-memory merge, or NCCL all-reduce)")
     args = ap.parse_args()
+    args.rows = args.rows or WORKLOADS[args.workload]["rows"]
+    args.cols = args.cols or WORKLOADS[args.workload]["cols"]
+    if args.steps is None:
+        args.steps = 100 if args.impl == "ours" else 5
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference_arm(args)
-    else:
-        run_gpu(args)
+        return 0
+    return run_gpu(args)
 
 
 if __name__ == "__main__":
-    main()
+    sys.exit(main())

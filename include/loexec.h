@@ -28,7 +28,10 @@
  *   - there is NO CPU fallback: without a usable CUDA device lo_init fails with
  *     LO_ERR_NO_DEVICE and nothing else can be called.
  *   - re-entrant: no mutable global state except the thread-local error string;
- *     concurrent calls on one lo_ctx are allowed when they use different streams.
+ *     concurrent calls on one lo_ctx are allowed when they use different streams.  No entry point
+ *     synchronises the whole device: a call waits only for the stream it was given (or the context's own).
+ *   - several GPUs: a lo_group (below) owns the peer mappings, the merge buffers and the optional NCCL
+ *     communicator; lo_group_* calls take one table / stream per LOCAL member device.
  */
 #ifndef LOEXEC_H
 #define LOEXEC_H
@@ -40,7 +43,7 @@
 extern "C" {
 #endif
 
-#define LO_ABI_VERSION 1
+#define LO_ABI_VERSION 2
 
 #define LO_OK                    0
 #define LO_ERR_INVALID          -1   /* bad argument (message says which)              */
@@ -56,13 +59,11 @@ extern "C" {
 #define LO_U8  3   /* unsigned byte */
 #define LO_U32 4   /* dictionary codes (host entry points only) */
 
-/* synthetic generators (oracle/synth.py and oracle/bsem.c hold the CPU twins) */
+/* synthetic generators (oracle/bsem.c and oracle/bsem_numpy.py hold the bit-identical CPU twins) */
 #define LO_SYNTH_UNIFORM   0  /* f64: lo + (hi-lo) * (splitmix64(...)>>11) * 2^-53            */
-#define LO_SYNTH_EDGES     1  /* UNIFORM + special values at row % 1000003 == col            */
+#define LO_SYNTH_EDGES     1  /* UNIFORM + special values where row % 1009 == col % 1009       */
 #define LO_SYNTH_CONSTCOL  2  /* EDGES + column 0 constant (contention worst case)           */
 #define LO_SYNTH_MNIST_U8  3  /* u8: 28x28 image columns, border 0, ~80 % zeros overall      */
-
-#define LO_HIST_PEER_COUNTS 1 /* counts_dev may be PEER memory (lo_ipc_open): flush with system-scope REDs */
 
 #define LO_MAX_BINS 256       /* per-thread byte-counter histograms hold <= 256 bins          */
 
@@ -76,7 +77,7 @@ typedef struct lo_table lo_table;  /* columnar table: ncols slabs of nrows eleme
  *   lo/hi are HOST arrays of k floats.  Counts are uint64, layout [k][nbins]. */
 typedef struct lo_hist_spec {
     int32_t      nbins;     /* 1..LO_MAX_BINS */
-    int32_t      flags;     /* 0, or LO_HIST_PEER_COUNTS */
+    int32_t      flags;     /* must be 0 */
     const float *lo;        /* k lower edges  */
     const float *hi;        /* k upper edges (closed) ; hi[j] > lo[j], both finite */
 } lo_hist_spec;
@@ -120,8 +121,9 @@ int lo_table_info(const lo_table *t, int *dtype, int64_t *nrows, int32_t *ncols,
 /* host <-> device, one column slab (or a row range of it) at a time; synchronous */
 int lo_table_upload_col(lo_ctx *ctx, lo_table *t, int32_t col, int64_t row0,
                         const void *host, int64_t nrows);
+/* ordered after everything already enqueued on `stream` (NULL = the context's stream); waits for that stream only */
 int lo_table_download_col(lo_ctx *ctx, const lo_table *t, int32_t col, int64_t row0,
-                          void *host, int64_t nrows);
+                          void *host, int64_t nrows, void *stream);
 /* fill every column on the device with the counter-based generator; row r of this table is
  * global row (row_offset + r), so any shard regenerates its own range. */
 int lo_table_fill_synthetic_dev(lo_ctx *ctx, lo_table *t, int kind, uint64_t seed,
@@ -180,34 +182,77 @@ int lo_project_cast_hist_host(lo_ctx *ctx, const double *const *in_cols, int64_t
 int lo_hist_u8_cols_host(lo_ctx *ctx, const uint8_t *const *in_cols, int64_t nrows, int32_t k,
                          uint64_t *counts, lo_host_timing *timing);
 
-/* ---- peer-memory histogram merge (multi-GPU, one process per GPU) -----------------------------------
- * Instead of "local counts + all-reduce", every rank's fused kernel can flush its per-tile bin sums with
- * RED.64 straight into ONE rank's count matrix over NVLink (spec.flags = LO_HIST_PEER_COUNTS): the merge
- * is fused into the kernel's own flush and costs no extra pass.  These calls provide the plumbing:
- * CUDA-IPC export/open of a device buffer and stream-ordered release/acquire flags.
- * handle: 64 bytes (cudaIpcMemHandle_t).  lo_ipc_open must run in a DIFFERENT process than the export. */
-int lo_ipc_export(lo_ctx *ctx, void *dev_ptr, void *handle64);
-int lo_ipc_open(lo_ctx *ctx, const void *handle64, void **dev_ptr);
-int lo_ipc_close(lo_ctx *ctx, void *dev_ptr);
-/* raw device scratch (zeroed) for flags / shared count matrices */
-int lo_dev_alloc(lo_ctx *ctx, size_t bytes, void **dev_ptr);
-int lo_dev_free(lo_ctx *ctx, void *dev_ptr);
-/* after everything already enqueued on `stream`: fence (system scope) + release-add `inc` to *flag
- * (flag may be peer memory) */
-int lo_flag_add_dev(lo_ctx *ctx, uint64_t *flag, uint64_t inc, void *stream);
-/* the same for up to 16 flags at once (one launch) */
-int lo_flag_add_many_dev(lo_ctx *ctx, uint64_t *const *flags, int32_t n, uint64_t inc, void *stream);
-/* the root's whole per-step epilogue in one launch: wait *arrived >= target (bounded), move
- * shared_counts[n] to result[n], re-zero shared_counts, release-add 1 to each peer's "clean" flag */
-int lo_peer_root_epilogue_dev(lo_ctx *ctx, const uint64_t *arrived, uint64_t target, uint32_t timeout_ms,
-                              uint64_t *timed_out_dev, uint64_t *shared_counts, uint64_t *result, int64_t n,
-                              uint64_t *const *peer_clean_flags, int32_t npeers, void *stream);
-int lo_dev_copy_dev(lo_ctx *ctx, void *dst, const void *src, size_t bytes, void *stream);
-/* make `stream` wait until *flag >= target (acquire, system scope).  Bounded: after timeout_ms the wait
- * gives up and increments *timed_out_dev (device uint64) so a lost peer cannot hang the GPU. */
-int lo_flag_wait_dev(lo_ctx *ctx, const uint64_t *flag, uint64_t target, uint32_t timeout_ms,
-                     uint64_t *timed_out_dev, void *stream);
-int lo_dev_read_u64(lo_ctx *ctx, const uint64_t *dev_ptr, int64_t n, uint64_t *host, void *stream);
+/* ---- several GPUs: row-range shards, one merged count matrix ------------------------------------------
+ * The reference has no multi-device path (one mongod pipeline per field, histogram_image/histogram.py:31-36; three
+ * single-core Spark executors, projection_image/server.py:58-60).  Here rows are range-sharded over the GPUs of one
+ * box and the per-GPU partial histograms are merged INSIDE the streaming kernel: every device accumulates its own
+ * matrix, the CTA that finishes a column's last tile pushes that column's bins into the root device's matrix with
+ * system-scope RED.64 over NVLink, the last pusher release-adds an arrival counter, and the root's last CTA moves the
+ * merged matrix out, re-zeroes and signals the peers — one kernel launch per device per step, no separate collective
+ * (LO_MERGE_PEER).  LO_MERGE_NCCL is the conventional form: local matrix + one ncclAllReduce(uint64, sum) on the
+ * same stream, through the libnccl.so.2 found at run time (dlopen; the library does not link against NCCL).
+ *
+ * Two ways to form a group:
+ *   - lo_group_create_local: ONE process drives several devices (what a single microservice process does on an
+ *     8-GPU box); peer access is enabled directly.
+ *   - lo_group_rank_begin / lo_group_rank_connect: one process per device (torchrun-style).  As with
+ *     ncclGetUniqueId / ncclCommInitRank the library produces an opaque blob per rank, the launcher's own
+ *     out-of-band channel gathers the W blobs, and every rank connects with all of them (CUDA IPC inside).
+ * All members must issue the same sequence of lo_group_* calls.  Member 0 / rank 0 is the root. */
+typedef struct lo_group lo_group;
+#define LO_GROUP_BLOB_BYTES 512
+#define LO_GROUP_MAX_DEVICES 16
+#define LO_GROUP_MAX_COUNTS  262144   /* entries of the largest merged matrix (1024 byte columns x 256) */
+#define LO_MERGE_AUTO 0   /* peer-memory merge when every pair of devices has peer access, else NCCL */
+#define LO_MERGE_PEER 1
+#define LO_MERGE_NCCL 2
+#define LO_GROUP_BCAST 1  /* call flag: every member receives the merged matrix (all-reduce); default: root only */
+
+int lo_group_create_local(lo_ctx *const *ctxs, int32_t n, int32_t merge, lo_group **out);
+int lo_group_rank_begin(lo_ctx *ctx, int32_t rank, int32_t world, int32_t merge, lo_group **out,
+                        void *blob /* LO_GROUP_BLOB_BYTES, filled */);
+int lo_group_rank_connect(lo_group *g, const void *blobs /* world * LO_GROUP_BLOB_BYTES, rank order */);
+int lo_group_destroy(lo_group *g);
+/* world size, members driven by this process, the merge actually in use (LO_MERGE_PEER / LO_MERGE_NCCL) */
+int lo_group_info(const lo_group *g, int32_t *world, int32_t *nlocal, int32_t *merge);
+/* rows [begin, end) of a `total_rows` table owned by member `index`; interior cuts are multiples of 32 rows */
+int lo_group_shard(const lo_group *g, int64_t total_rows, int32_t index, int64_t *begin, int64_t *end);
+
+/* The hot path over the group.  in[i] / out[i] / streams[i]: the shard, output table (or out == NULL) and stream
+ * (or streams == NULL: each context's own) of LOCAL member i.  Asynchronous.  The merged k x nbins matrix of the
+ * step lands in the group's result buffer on the root (on every member with LO_GROUP_BCAST or LO_MERGE_NCCL);
+ * read it with lo_group_result.  k <= 128 (f64) / 1024 (u8) per call. */
+int lo_group_project_cast_hist_dev(lo_group *g, const lo_table *const *in, const int32_t *col_idx, int32_t k,
+                                   lo_table *const *out, const lo_hist_spec *spec, int32_t flags,
+                                   void *const *streams);
+int lo_group_hist_u8_cols_dev(lo_group *g, const lo_table *const *in, const int32_t *col_idx, int32_t k,
+                              int32_t flags, void *const *streams);
+/* range pre-pass over all shards: merged per-column min / max / finite count of the cast values;
+ * read with lo_group_result(n = 3*k) and decode with lo_minmax_decode.  Always delivered to every member. */
+int lo_group_minmax_cast_dev(lo_group *g, const lo_table *const *in, const int32_t *col_idx, int32_t k,
+                             void *const *streams);
+/* host buffers in / out, rows of THIS process only: with a local group the library cuts [0, nrows) into one row range
+ * per member and drives one H2D / kernel / D2H pipeline per device (a host thread each); with a rank group every
+ * rank passes its own shard.  counts: merged k x nbins matrix (root / member 0; every rank with LO_GROUP_BCAST). */
+int lo_group_project_cast_hist_host(lo_group *g, const double *const *in_cols, int64_t nrows, int32_t k,
+                                    float *const *out_cols, const lo_hist_spec *spec, uint64_t *counts,
+                                    int32_t flags, lo_host_timing *timing);
+int lo_group_hist_u8_cols_host(lo_group *g, const uint8_t *const *in_cols, int64_t nrows, int32_t k,
+                               uint64_t *counts, int32_t flags, lo_host_timing *timing);
+/* waits for the last step on local member `member` and copies the first n entries of its result buffer.
+ * LO_ERR_INVALID when that member holds no result (non-root without LO_GROUP_BCAST / NCCL). */
+int lo_group_result(lo_group *g, int32_t member, int64_t n, uint64_t *host);
+/* device pointer of a local member's result buffer (valid until lo_group_destroy; contents: the last step) */
+int lo_group_result_dev(lo_group *g, int32_t member, uint64_t **dev_ptr);
+/* device-side barrier over all members on the given streams (a few microseconds of skew instead of a host barrier's
+ * tens): every stream continues once all W devices have reached it.  Peer merge only. */
+int lo_group_barrier_dev(lo_group *g, void *const *streams);
+/* number of bounded device-side waits that gave up (a lost or wedged peer) since the group was formed; must be 0 */
+int lo_group_timeouts(lo_group *g, uint64_t *out);
+
+/* pin the CALLING thread to the CPUs local to the context's GPU (PCI device's NUMA node, from sysfs): pinned host
+ * buffers allocated and first touched afterwards land on the memory next to the GPU's PCIe root. */
+int lo_ctx_bind_numa(lo_ctx *ctx, int32_t *node_out, int32_t *ncpus_out);
 
 /* Exact value counts of one dictionary-encoded column (R-semantics `$group`/`$sum:1`,
  * histogram_image/histogram.py:31-36, for columns with more than 256 distinct keys):

@@ -26,9 +26,13 @@ LO_ERR_ALIGNMENT = -6
 LO_F64, LO_F32, LO_U8, LO_U32 = 1, 2, 3, 4
 LO_SYNTH_UNIFORM, LO_SYNTH_EDGES, LO_SYNTH_CONSTCOL, LO_SYNTH_MNIST_U8 = 0, 1, 2, 3
 LO_MAX_BINS = 256
-LO_HIST_PEER_COUNTS = 1
+LO_MERGE_AUTO, LO_MERGE_PEER, LO_MERGE_NCCL = 0, 1, 2
+LO_GROUP_BCAST = 1
+LO_GROUP_BLOB_BYTES = 512
+LO_GROUP_MAX_DEVICES = 16
+LO_GROUP_MAX_COUNTS = 262144
 LO_NUM_FLOAT, LO_NUM_INTEGER, LO_NUM_EMPTY, LO_NUM_INVALID, LO_NUM_UNSUPPORTED = 0, 1, 2, 3, 4
-LO_ABI_VERSION = 1
+LO_ABI_VERSION = 2
 
 _ERR_NAMES = {
     LO_ERR_INVALID: "LO_ERR_INVALID", LO_ERR_CUDA: "LO_ERR_CUDA", LO_ERR_NOMEM: "LO_ERR_NOMEM",
@@ -76,7 +80,7 @@ SIGNATURES = {
     "lo_table_info": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int64), C.POINTER(C.c_int32),
                                 C.POINTER(C.c_int64), C.POINTER(_P)]),
     "lo_table_upload_col": (C.c_int, [_P, _P, C.c_int32, C.c_int64, _P, C.c_int64]),
-    "lo_table_download_col": (C.c_int, [_P, _P, C.c_int32, C.c_int64, _P, C.c_int64]),
+    "lo_table_download_col": (C.c_int, [_P, _P, C.c_int32, C.c_int64, _P, C.c_int64, _P]),
     "lo_table_fill_synthetic_dev": (C.c_int, [_P, _P, C.c_int, C.c_uint64, C.c_int64, C.c_double, C.c_double, _P]),
     "lo_table_checksum": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.POINTER(C.c_uint64)]),
     "lo_selftest_fastdiv": (C.c_int, [_P, C.c_float, C.c_float, C.c_int32, C.POINTER(C.c_int), C.POINTER(C.c_uint64)]),
@@ -92,17 +96,24 @@ SIGNATURES = {
     "lo_project_cast_hist_host": (C.c_int, [_P, C.POINTER(_P), C.c_int64, C.c_int32, C.POINTER(_P),
                                             C.POINTER(HistSpec), _P, C.POINTER(HostTiming)]),
     "lo_hist_u8_cols_host": (C.c_int, [_P, C.POINTER(_P), C.c_int64, C.c_int32, _P, C.POINTER(HostTiming)]),
-    "lo_ipc_export": (C.c_int, [_P, _P, _P]),
-    "lo_ipc_open": (C.c_int, [_P, _P, C.POINTER(_P)]),
-    "lo_ipc_close": (C.c_int, [_P, _P]),
-    "lo_dev_alloc": (C.c_int, [_P, C.c_size_t, C.POINTER(_P)]),
-    "lo_dev_free": (C.c_int, [_P, _P]),
-    "lo_flag_add_dev": (C.c_int, [_P, _P, C.c_uint64, _P]),
-    "lo_flag_add_many_dev": (C.c_int, [_P, C.POINTER(_P), C.c_int32, C.c_uint64, _P]),
-    "lo_peer_root_epilogue_dev": (C.c_int, [_P, _P, C.c_uint64, C.c_uint32, _P, _P, _P, C.c_int64, C.POINTER(_P), C.c_int32, _P]),
-    "lo_dev_copy_dev": (C.c_int, [_P, _P, _P, C.c_size_t, _P]),
-    "lo_flag_wait_dev": (C.c_int, [_P, _P, C.c_uint64, C.c_uint32, _P, _P]),
-    "lo_dev_read_u64": (C.c_int, [_P, _P, C.c_int64, _P, _P]),
+    "lo_group_create_local": (C.c_int, [C.POINTER(_P), C.c_int32, C.c_int32, C.POINTER(_P)]),
+    "lo_group_rank_begin": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_P), _P]),
+    "lo_group_rank_connect": (C.c_int, [_P, _P]),
+    "lo_group_destroy": (C.c_int, [_P]),
+    "lo_group_info": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "lo_group_shard": (C.c_int, [_P, C.c_int64, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "lo_group_project_cast_hist_dev": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int32), C.c_int32, C.POINTER(_P),
+                                                 C.POINTER(HistSpec), C.c_int32, C.POINTER(_P)]),
+    "lo_group_hist_u8_cols_dev": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.POINTER(_P)]),
+    "lo_group_minmax_cast_dev": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int32), C.c_int32, C.POINTER(_P)]),
+    "lo_group_project_cast_hist_host": (C.c_int, [_P, C.POINTER(_P), C.c_int64, C.c_int32, C.POINTER(_P),
+                                                  C.POINTER(HistSpec), _P, C.c_int32, C.POINTER(HostTiming)]),
+    "lo_group_hist_u8_cols_host": (C.c_int, [_P, C.POINTER(_P), C.c_int64, C.c_int32, _P, C.c_int32, C.POINTER(HostTiming)]),
+    "lo_group_result": (C.c_int, [_P, C.c_int32, C.c_int64, _P]),
+    "lo_group_result_dev": (C.c_int, [_P, C.c_int32, C.POINTER(_P)]),
+    "lo_group_barrier_dev": (C.c_int, [_P, C.POINTER(_P)]),
+    "lo_group_timeouts": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
+    "lo_ctx_bind_numa": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "lo_value_counts_u32_host": (C.c_int, [_P, _P, C.c_int64, C.c_uint32, _P, C.POINTER(HostTiming)]),
     "lo_value_counts_f64_host": (C.c_int, [_P, _P, C.c_int64, _P, _P, C.c_int64, C.POINTER(C.c_int64), C.POINTER(HostTiming)]),
     "lo_value_counts_str_host": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P, C.c_int64, C.POINTER(C.c_int64), C.POINTER(HostTiming)]),

@@ -45,7 +45,7 @@ def _stale(target: Path, sources: list[Path]) -> bool:
 
 
 def build_native(force: bool = False, verbose: bool = False) -> Path:
-    sources = [CSRC / "loexec.cu", CSRC / "kernels.cuh", CSRC / "parse_number.cuh", CSRC / "pow5_table.inc",
+    sources = [CSRC / "loexec.cu", CSRC / "group.inc", CSRC / "kernels.cuh", CSRC / "parse_number.cuh", CSRC / "pow5_table.inc",
                ROOT / "include" / "loexec.h"]
     if not force and not _stale(LIB_PATH, sources):
         return LIB_PATH

@@ -68,8 +68,6 @@ constexpr int kMaxColsU8    = 1024;
 struct ColsF64 {
     int32_t k;
     int32_t nbins;
-    int32_t sys_scope;   // 1: counts may live in a PEER GPU's memory -> RED.64 at system scope
-    int32_t pad_;
     int32_t col[kMaxColsF64];
     float   lo[kMaxColsF64];
     float   hi[kMaxColsF64];
@@ -79,6 +77,42 @@ struct ColsF64 {
 struct ColsU8 {
     int32_t k;
     int32_t col[kMaxColsU8];
+};
+
+// blockIdx -> (projected column, row range).  Two segments per column: `tiles_a` tiles of `batches_a` pipeline
+// batches each cover rows [0, tiles_a * rows(batches_a)), then `tiles_b` SHORT tiles of `batches_b` batches cover the
+// rest.  All segment-A blocks come first in blockIdx (= dispatch) order, so the last wave of the grid is made of short
+// tiles and the tail during which the machine drains is a fraction of a full tile (the 12.5 M-row shard of the
+// 8-GPU run lost 4.6 % to a 23rd wave that was 5 % full).  rows(b) = b * kPfBatch * kThreads * kVec.
+struct TileMap {
+    unsigned tiles_a, tiles_b;     // tiles per column in each segment (tiles_b may be 0)
+    unsigned blocks_a;             // k * tiles_a
+    int      batches_a, batches_b; // pipeline batches per tile: even, 2 .. kPfBatches
+};
+
+// One step of the multi-GPU histogram merge, executed INSIDE the streaming kernel (loexec.cu: lo_group_*).
+// Every device accumulates into its own `local` matrix; the CTA that finishes the last tile of a column pushes
+// that column's bins into the root GPU's `shared` matrix (system-scope RED.64 over NVLink / peer mapping), the CTA
+// that pushes the last column release-adds the root's `arrived` counter, and on the root that same CTA waits for
+// all W arrivals, moves the merged matrix to `result` (and to every peer's with bcast), re-zeroes `shared` and
+// release-adds each peer's `clean` counter.  No separate flag / memset / epilogue launches: one launch per step.
+constexpr int kMaxPeers = 15;
+struct GroupStep {
+    int mode;                          // 0: no group (plain accumulate into counts);  1: merge as described
+    int is_root, npeers, epilogue_in_kernel;
+    unsigned long long *local;         // this device's accumulate matrix (zero at entry, left zero at exit)
+    unsigned long long *shared;        // root's merge matrix of this step's parity (peer-mapped on the others)
+    unsigned long long *arrived;       // root's arrival counter of this parity
+    const unsigned long long *clean;   // this device's "root has re-zeroed shared" counter (nullptr on the root)
+    unsigned long long clean_target;   // push only once *clean >= clean_target
+    unsigned int *col_ticket;          // [k] tiles finished per column (self-resetting)
+    unsigned int *done_ticket;         // columns pushed (self-resetting)
+    unsigned long long arrive_target;  // root: W * (step / 2 + 1)
+    unsigned long long *result;        // root: merged matrix of the finished step
+    unsigned long long timeout_ns;     // bound on every wait; a lost peer raises *timed_out instead of hanging the GPU
+    unsigned long long *timed_out;
+    unsigned long long *peer_clean[kMaxPeers];    // root: the peers' clean counters
+    unsigned long long *peer_result[kMaxPeers];   // root: the peers' result matrices (bcast), else nullptr
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -204,8 +238,7 @@ __device__ __forceinline__ void zero_private(uint32_t *smem, int rows) {
 // Each private byte is <= 255 and a row holds kThreads = 256 words: a lane sums 8 words into
 // packed 16-bit halves (<= 2040), the 32-lane butterfly keeps them <= 65280 — no overflow.
 __device__ __forceinline__ void fold_and_flush(uint32_t *smem, int rows, int nbins,
-                                               unsigned long long *counts /* this column's bins */,
-                                               bool sys_scope = false) {
+                                               unsigned long long *counts /* this column's bins */) {
     uint32_t *folded = smem + kHistRows * kThreads;   // 256 words
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     __syncthreads();
@@ -233,13 +266,110 @@ __device__ __forceinline__ void fold_and_flush(uint32_t *smem, int rows, int nbi
     __syncthreads();
     if ((int)threadIdx.x < nbins) {
         uint32_t c = folded[threadIdx.x];
+        if (c) atomicAdd(counts + threadIdx.x, (unsigned long long)c);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// multi-GPU merge, in-kernel (GroupStep).  Memory-model notes: the per-tile REDs into `local` are relaxed, gpu scope;
+// bar.sync + thread 0's fence + its ticket atomic publish them to whichever CTA takes the column's last ticket
+// (the threadFenceReduction pattern).  That CTA's pushes are system-scope REDs; bar.sync + fence.sys + the
+// done-ticket atomic order them before the release-add on `arrived` issued by the CTA that takes the last done ticket
+// (causality order is transitive over these synchronizes-with edges), and the root acquires `arrived` at system scope.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long ld_relaxed_gpu(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_sys_add(unsigned long long *p, unsigned long long v) {
+    asm volatile("red.release.sys.global.add.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// spin until *flag >= target; gives up after timeout_ns and raises *timed_out (returns false)
+__device__ __forceinline__ bool wait_flag_ge(const unsigned long long *flag, unsigned long long target,
+                                             unsigned long long timeout_ns, unsigned long long *timed_out) {
+    if (ld_acquire_sys(flag) >= target) return true;
+    const unsigned long long t0 = globaltimer_ns();
+    for (;;) {
+        if (ld_acquire_sys(flag) >= target) return true;
+        if (globaltimer_ns() - t0 > timeout_ns) { atomicAdd(timed_out, 1ull); return false; }
+        __nanosleep(64);
+    }
+}
+
+// root: all W devices have pushed -> move the merged matrix out, re-zero it, tell the peers.  One CTA (any size).
+__device__ __forceinline__ void group_root_epilogue(const GroupStep &G, int n, int first, int stride, bool signal) {
+    for (int i = first; i < n; i += stride) {
+        // the peers' REDs were performed by this GPU's L2: read them there
+        const unsigned long long c = ld_relaxed_sys(G.shared + i);
+        G.result[i] = c;
+        for (int p = 0; p < G.npeers; ++p)
+            if (G.peer_result[p]) G.peer_result[p][i] = c;
+        G.shared[i] = 0ull;
+    }
+    if (signal) {
+        __syncthreads();
+        __threadfence_system();
+        if ((int)threadIdx.x < G.npeers) red_release_sys_add(G.peer_clean[threadIdx.x], 1ull);
+    }
+}
+
+// Called by every thread of a CTA after its tile's REDs into G.local were issued.  j: projected column, nb: its bins,
+// k: columns of this launch.  Uses one word of shared memory (`sflag`, any smem word the caller no longer needs).
+__device__ __forceinline__ void group_finish_column(const GroupStep &G, unsigned j, int nb, int k, unsigned tiles_per_col,
+                                                    volatile uint32_t *sflag) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        *sflag = (atomicAdd(G.col_ticket + j, 1u) == tiles_per_col - 1u) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (*sflag == 0u) return;
+    // last tile of column j on this device: every tile's REDs into local[j][*] are visible after this fence
+    __threadfence();
+    if (threadIdx.x == 0) {
+        G.col_ticket[j] = 0u;
+        if (G.clean) wait_flag_ge(G.clean, G.clean_target, G.timeout_ns, G.timed_out);   // root re-zeroed `shared`?
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < nb; b += blockDim.x) {
+        unsigned long long *src = G.local + (long long)j * nb + b;
+        const unsigned long long c = ld_relaxed_gpu(src);
         if (c) {
-            // sys_scope: the count matrix is another GPU's memory mapped over NVLink (lo_ipc_open); the
-            // reduction is then performed by the owner's L2, i.e. the histogram merge rides on the flush
-            if (sys_scope) atomicAdd_system(counts + threadIdx.x, (unsigned long long)c);
-            else           atomicAdd(counts + threadIdx.x, (unsigned long long)c);
+            atomicAdd_system(G.shared + (long long)j * nb + b, c);     // the owner's L2 performs the reduction
+            *src = 0ull;                                               // local matrix is clean for the next step
         }
     }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        const bool last = atomicAdd(G.done_ticket, 1u) == (unsigned)k - 1u;
+        if (last) {
+            *G.done_ticket = 0u;
+            __threadfence_system();
+            red_release_sys_add(G.arrived, 1ull);
+        }
+        *sflag = (last && G.is_root && G.epilogue_in_kernel) ? 2u : 0u;
+        if (*sflag == 2u && !wait_flag_ge(G.arrived, G.arrive_target, G.timeout_ns, G.timed_out)) *sflag = 3u;
+    }
+    __syncthreads();
+    if (*sflag == 2u) group_root_epilogue(G, k * nb, threadIdx.x, blockDim.x, true);
+    else if (*sflag == 3u && (int)threadIdx.x < G.npeers) red_release_sys_add(G.peer_clean[threadIdx.x], 1ull);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -253,14 +383,29 @@ template <int OUT, bool HIST, bool ALIGNED, bool FASTDIV>
 __global__ void __launch_bounds__(kThreads, LO_MIN_CTAS)
 k_project_cast_hist(const char *__restrict__ in_base, long long in_pitch,
                     char *__restrict__ out_base, long long out_pitch,
-                    long long nrows, unsigned tiles_per_col,
-                    unsigned long long *__restrict__ counts,
-                    const __grid_constant__ ColsF64 P) {
+                    long long nrows, unsigned long long *__restrict__ counts,
+                    const __grid_constant__ ColsF64 P, const __grid_constant__ TileMap M,
+                    const __grid_constant__ GroupStep G) {
     extern __shared__ uint32_t smem[];
-    const unsigned j    = blockIdx.x / tiles_per_col;
-    const unsigned tile = blockIdx.x - j * tiles_per_col;
-    const long long r0  = (long long)tile * kTileRows;
-    const long long n   = min((long long)kTileRows, nrows - r0);   // rows in this tile (> 0)
+    // blockIdx -> (column j, rows [r0, r0 + n)): full-size tiles first, the short tiles of the tapered tail last
+    unsigned j, tile;
+    int nbatches;
+    long long r0;
+    if (blockIdx.x < M.blocks_a) {
+        j = blockIdx.x / M.tiles_a;
+        tile = blockIdx.x - j * M.tiles_a;
+        nbatches = M.batches_a;
+        r0 = (long long)tile * (M.batches_a * (kPfBatch * kThreads * kVec));
+    } else {
+        const unsigned b = blockIdx.x - M.blocks_a;
+        j = b / M.tiles_b;
+        tile = b - j * M.tiles_b;
+        nbatches = M.batches_b;
+        r0 = (long long)M.tiles_a * (M.batches_a * (kPfBatch * kThreads * kVec)) +
+             (long long)tile * (M.batches_b * (kPfBatch * kThreads * kVec));
+    }
+    const long long tile_rows = (long long)nbatches * (kPfBatch * kThreads * kVec);
+    const long long n = min(tile_rows, nrows - r0);   // rows in this tile (> 0)
 
     const double *in = reinterpret_cast<const double *>(in_base + (long long)P.col[j] * in_pitch) + r0;
     float  *out32 = nullptr;
@@ -280,8 +425,8 @@ k_project_cast_hist(const char *__restrict__ in_base, long long in_pitch,
         // a thread only touches its own words until fold_and_flush: no barrier needed here
     }
 
-    if (ALIGNED && n == kTileRows) {
-        // full tile (all but the last tile of a column): no bounds checks, register-pipelined loads.
+    if (ALIGNED && n == tile_rows) {
+        // full tile: no bounds checks, register-pipelined loads.
         // vector index of (batch b, slot u) = (b*kPfBatch + u)*kThreads + tid  ->  warp-contiguous 1 KiB
         double v[kPfBuf][kPfBatch][4];
         const double *src = in + (long long)threadIdx.x * kVec;
@@ -291,12 +436,12 @@ k_project_cast_hist(const char *__restrict__ in_base, long long in_pitch,
             for (int u = 0; u < kPfBatch; ++u)
                 ldg256_stream(src + (long long)(pb * kPfBatch + u) * kThreads * kVec, v[pb][u]);
 #pragma unroll 1
-        for (int b0 = 0; b0 < kPfBatches; b0 += kPfBuf) {
+        for (int b0 = 0; b0 < nbatches; b0 += kPfBuf) {
 #pragma unroll
             for (int s = 0; s < kPfBuf; ++s) {
                 const int b  = b0 + s;                 // batch being processed, lives in buffer s
                 const int nb = b + kPfBuf - 1;         // batch to fetch, into buffer (s + kPfBuf - 1) % kPfBuf
-                if (nb < kPfBatches) {
+                if (nb < nbatches) {
 #pragma unroll
                     for (int u = 0; u < kPfBatch; ++u)
                         ldg256_stream(src + (long long)(nb * kPfBatch + u) * kThreads * kVec, v[(s + kPfBuf - 1) % kPfBuf][u]);
@@ -367,7 +512,15 @@ k_project_cast_hist(const char *__restrict__ in_base, long long in_pitch,
         }
     }
 
-    if (HIST) fold_and_flush(smem, rows, P.nbins, counts + (long long)j * P.nbins, P.sys_scope != 0);
+    if (HIST) {
+        if (G.mode == 0) {
+            fold_and_flush(smem, rows, P.nbins, counts + (long long)j * P.nbins);
+        } else {
+            // multi-GPU merge riding on the flush: accumulate on this device, the column's last tile pushes to the root
+            fold_and_flush(smem, rows, P.nbins, G.local + (long long)j * P.nbins);
+            group_finish_column(G, j, P.nbins, P.k, M.tiles_a + M.tiles_b, smem);
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -533,10 +686,7 @@ k_project_cast_hist_tma(const char *__restrict__ in_base, long long in_pitch,
         if ((int)threadIdx.x < P.nbins) {
             const uint32_t c = folded[threadIdx.x];
             unsigned long long *dst = counts + (long long)j * P.nbins + threadIdx.x;
-            if (c) {
-                if (P.sys_scope) atomicAdd_system(dst, (unsigned long long)c);
-                else             atomicAdd(dst, (unsigned long long)c);
-            }
+            if (c) atomicAdd(dst, (unsigned long long)c);
         }
     }
 }
@@ -617,7 +767,7 @@ template <bool ALIGNED>
 __global__ void __launch_bounds__(kThreads, 3)
 k_hist_u8_cols(const uint8_t *__restrict__ in_base, long long in_pitch, long long nrows,
                unsigned tiles_per_col, unsigned long long *__restrict__ counts,
-               const __grid_constant__ ColsU8 P) {
+               const __grid_constant__ ColsU8 P, const __grid_constant__ GroupStep G) {
     extern __shared__ uint32_t smem[];
     const unsigned j    = blockIdx.x / tiles_per_col;
     const unsigned tile = blockIdx.x - j * tiles_per_col;
@@ -656,7 +806,12 @@ k_hist_u8_cols(const uint8_t *__restrict__ in_base, long long in_pitch, long lon
             bump(priv, ldg8_stream(in + e));
         }
     }
-    fold_and_flush(smem, kHistRows, 256, counts + (long long)j * 256);
+    if (G.mode == 0) {
+        fold_and_flush(smem, kHistRows, 256, counts + (long long)j * 256);
+    } else {
+        fold_and_flush(smem, kHistRows, 256, G.local + (long long)j * 256);
+        group_finish_column(G, j, 256, P.k, tiles_per_col, smem);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -731,68 +886,74 @@ __global__ void k_fill_u8_mnist(uint8_t *base, long long pitch, long long nrows,
 }
 
 // ---------------------------------------------------------------------------------------------
-// cross-GPU flags for the peer-memory histogram merge (sharding.PeerReduce)
+// multi-GPU merge: the launches that are NOT the streaming kernel
 // ---------------------------------------------------------------------------------------------
-// stream-ordered after the kernel whose REDs it publishes: fence, then release-add on a (peer) flag
-__global__ void k_flag_add(unsigned long long *flag, unsigned long long inc) {
-    __threadfence_system();
-    asm volatile("red.release.sys.global.add.u64 [%0], %1;" :: "l"(flag), "l"(inc) : "memory");
+// root epilogue as its own multi-CTA launch, for count matrices too large for one CTA to move in a few
+// microseconds (config M: 784 x 256 counts = 1.5 MiB).  Every CTA waits for the W arrivals itself, moves its slice,
+// and the CTA that finishes last tells the peers.
+__global__ void __launch_bounds__(256)
+k_group_root_epilogue(const __grid_constant__ GroupStep G, int n) {
+    __shared__ int ok, last;
+    if (threadIdx.x == 0) ok = wait_flag_ge(G.arrived, G.arrive_target, G.timeout_ns, G.timed_out) ? 1 : 0;
+    __syncthreads();
+    if (ok) group_root_epilogue(G, n, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, false);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        last = atomicAdd(G.done_ticket, 1u) == gridDim.x - 1u;
+        if (last) { *G.done_ticket = 0u; __threadfence_system(); }
+    }
+    __syncthreads();
+    if (last && (int)threadIdx.x < G.npeers) red_release_sys_add(G.peer_clean[threadIdx.x], 1ull);
 }
 
-struct FlagPtrs { unsigned long long *p[16]; int n; };
-__global__ void k_flag_add_many(const __grid_constant__ FlagPtrs F, unsigned long long inc) {
-    __threadfence_system();
-    if ((int)threadIdx.x < F.n)
-        asm volatile("red.release.sys.global.add.u64 [%0], %1;" :: "l"(F.p[threadIdx.x]), "l"(inc) : "memory");
+// merge of a small per-device vector that some other kernel(s) already accumulated into G.local (the *_host
+// pipelines, the min/max pre-pass): one CTA pushes it to the root, arrives, and on the root runs the epilogue.
+//   op 0: every element is a sum.   op 1: min/max pre-pass layout, elements 3j, 3j+1 are maxima, 3j+2 a sum.
+__global__ void __launch_bounds__(256)
+k_group_push(const __grid_constant__ GroupStep G, int n, int op) {
+    __shared__ int state;
+    if (threadIdx.x == 0 && G.clean) wait_flag_ge(G.clean, G.clean_target, G.timeout_ns, G.timed_out);
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const unsigned long long c = ld_relaxed_gpu(G.local + i);
+        if (c) {
+            if (op == 1 && (i % 3) != 2) atomicMax_system(G.shared + i, c);
+            else                         atomicAdd_system(G.shared + i, c);
+            G.local[i] = 0ull;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        red_release_sys_add(G.arrived, 1ull);
+        state = G.is_root ? (wait_flag_ge(G.arrived, G.arrive_target, G.timeout_ns, G.timed_out) ? 2 : 3) : 0;
+    }
+    __syncthreads();
+    if (state == 2) group_root_epilogue(G, n, threadIdx.x, blockDim.x, true);
+    else if (state == 3 && (int)threadIdx.x < G.npeers) red_release_sys_add(G.peer_clean[threadIdx.x], 1ull);
 }
 
-// spin until *flag >= target (acquire, system scope); gives up after ~timeout_ns and raises *timed_out
+// device-side barrier across the group: everybody release-adds the root's counter and spins on it (remote polling
+// over NVLink for the non-root devices).  Used to start a timed region on all GPUs within a few microseconds.
+__global__ void k_group_barrier(unsigned long long *root_counter, unsigned long long target, unsigned long long timeout_ns,
+                                unsigned long long *timed_out) {
+    __threadfence_system();
+    red_release_sys_add(root_counter, 1ull);
+    wait_flag_ge(root_counter, target, timeout_ns, timed_out);
+}
+
+// LO_MERGE_NCCL min/max pre-pass: result[0, n) holds the max-reduction, result[n, 2n) the sum-reduction of the same
+// vector; element 3j+2 (the finite count) is meaningful in the sum, the others in the max
+__global__ void k_minmax_compose(unsigned long long *result, int n) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+        if (i % 3 == 2) result[i] = result[n + i];
+}
+
+// a non-root device waits for the root's broadcast of step `target` (its clean counter doubles as "result ready")
 __global__ void k_flag_wait(const unsigned long long *flag, unsigned long long target, unsigned long long timeout_ns,
                             unsigned long long *timed_out) {
-    unsigned long long t0, now, v;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    for (;;) {
-        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
-        if (v >= target) return;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-        if (now - t0 > timeout_ns) { atomicAdd(timed_out, 1ull); return; }
-        __nanosleep(200);
-    }
-}
-
-// root's whole epilogue of one peer-merge step in ONE launch: wait for all ranks' arrivals, move the merged
-// counts to the result buffer, re-zero the shared buffer, tell every peer it is clean again
-__global__ void k_peer_root_epilogue(const unsigned long long *arrived, unsigned long long target,
-                                     unsigned long long timeout_ns, unsigned long long *timed_out,
-                                     unsigned long long *shared_counts, unsigned long long *result, int n,
-                                     const __grid_constant__ FlagPtrs peers) {
-    __shared__ int ok;
-    if (threadIdx.x == 0) {
-        unsigned long long t0, now, v;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-        ok = 1;
-        for (;;) {
-            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(arrived) : "memory");
-            if (v >= target) break;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-            if (now - t0 > timeout_ns) { atomicAdd(timed_out, 1ull); ok = 0; break; }
-            __nanosleep(100);
-        }
-    }
-    __syncthreads();
-    if (ok) {
-        // the peers' REDs were performed by this GPU's L2; read them back there (bypass L1)
-        for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            unsigned long long c;
-            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(c) : "l"(shared_counts + i) : "memory");
-            result[i] = c;
-            shared_counts[i] = 0ull;
-        }
-    }
-    __syncthreads();
-    __threadfence_system();
-    if ((int)threadIdx.x < peers.n)
-        asm volatile("red.release.sys.global.add.u64 [%0], %1;" :: "l"(peers.p[threadIdx.x]), "l"(1ull) : "memory");
+    wait_flag_ge(flag, target, timeout_ns, timed_out);
 }
 
 // exact value counts of dictionary codes (R-semantics $group on arbitrary columns): RED.64 per element;

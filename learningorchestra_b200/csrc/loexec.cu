@@ -7,6 +7,7 @@
 #include "kernels.cuh"
 
 #include <atomic>
+#include <cctype>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
@@ -70,6 +71,8 @@ struct lo_table {
     int       device;
 };
 
+constexpr int kSlots = 3;      // staging slots of the *_host pipeline: H2D of chunk c+1/c+2 overlaps kernel c and D2H c-1
+
 struct lo_ctx {
     int          device;
     int          sm_count;
@@ -80,12 +83,12 @@ struct lo_ctx {
     std::atomic<bool> use_tma{false};   // LOEXEC_TMA=1 or lo_set_tma(): stage slabs through smem with cp.async.bulk
     // *_host pipeline staging (one pipeline at a time per context)
     std::mutex   host_mu;
-    char        *stage_in[2]  = {nullptr, nullptr};
-    char        *stage_out[2] = {nullptr, nullptr};
+    char        *stage_in[kSlots]  = {nullptr, nullptr, nullptr};
+    char        *stage_out[kSlots] = {nullptr, nullptr, nullptr};
     size_t       stage_in_bytes = 0, stage_out_bytes = 0;
     unsigned long long *host_counts_dev = nullptr;
     size_t       host_counts_n = 0;
-    cudaEvent_t  ev_h2d[2], ev_k[2], ev_d2h[2];
+    cudaEvent_t  ev_h2d[kSlots], ev_k[kSlots], ev_d2h[kSlots];
 };
 
 namespace {
@@ -115,7 +118,7 @@ int check_cols(const lo_table *in, const int32_t *col_idx, int32_t k) {
 int check_spec(const lo_hist_spec *spec, int32_t k, float *w_out /* k */) {
     if (spec->nbins < 1 || spec->nbins > LO_MAX_BINS)
         return fail(LO_ERR_INVALID, "nbins = %d outside [1, %d]", spec->nbins, LO_MAX_BINS);
-    if (spec->flags & ~LO_HIST_PEER_COUNTS) return fail(LO_ERR_INVALID, "unknown lo_hist_spec.flags 0x%x", spec->flags);
+    if (spec->flags != 0) return fail(LO_ERR_INVALID, "unknown lo_hist_spec.flags 0x%x", spec->flags);
     if (!spec->lo || !spec->hi) return fail(LO_ERR_INVALID, "lo_hist_spec.lo / .hi is NULL");
     for (int j = 0; j < k; ++j) {
         const float lo = spec->lo[j], hi = spec->hi[j];
@@ -175,23 +178,54 @@ int configure_kernels() {
     return LO_OK;
 }
 
+// blockIdx -> tile map of one launch (kernels.cuh TileMap).  Grids of more than one wave get a tapered tail:
+// the last `tail_waves` waves' worth of rows is cut into short tiles (`tail_batches` pipeline batches instead of
+// kPfBatches), so the drain at the end of the launch costs a fraction of a full tile's time.  LOEXEC_TAIL_BATCHES
+// (0 = no taper) and LOEXEC_TAIL_WAVES override the defaults for measurements (scripts/tile_sweep.py).
+lo::TileMap make_tilemap(const lo_ctx *ctx, int64_t nrows, int32_t k) {
+    constexpr int64_t kBatchRows = (int64_t)lo::kPfBatch * lo::kThreads * lo::kVec;     // 5120
+    lo::TileMap M;
+    M.batches_a = lo::kPfBatches;
+    M.batches_b = lo::kPfBatches;
+    M.tiles_a = (unsigned)((nrows + lo::kTileRows - 1) / lo::kTileRows);
+    M.tiles_b = 0;
+    int tail_batches = 4;
+    double tail_waves = 1.0;
+    if (const char *e = getenv("LOEXEC_TAIL_BATCHES")) tail_batches = atoi(e);
+    if (const char *e = getenv("LOEXEC_TAIL_WAVES")) tail_waves = atof(e);
+    const int64_t slots = (int64_t)ctx->sm_count * LO_MIN_CTAS;
+    const int64_t full_tiles = nrows / lo::kTileRows;           // per column
+    if (tail_batches >= 2 && tail_batches < lo::kPfBatches && tail_batches % lo::kPfBuf == 0 && tail_waves > 0.0 &&
+        full_tiles * k > slots) {
+        int64_t tail_tiles = (int64_t)std::ceil(tail_waves * (double)slots / (double)k);   // full tiles per column -> short
+        tail_tiles = std::min(std::max<int64_t>(tail_tiles, 1), full_tiles);
+        const int64_t rows_a = (full_tiles - tail_tiles) * lo::kTileRows;
+        const int64_t rows_b = nrows - rows_a;
+        M.tiles_a = (unsigned)(full_tiles - tail_tiles);
+        M.batches_b = tail_batches;
+        M.tiles_b = (unsigned)((rows_b + tail_batches * kBatchRows - 1) / (tail_batches * kBatchRows));
+    }
+    M.blocks_a = M.tiles_a * (unsigned)k;
+    return M;
+}
+
+const lo::GroupStep kNoGroup = {};     // mode 0
+
 // one launch of the fused kernel over <= kMaxColsF64 projected columns
 template <int OUT, bool HIST>
 int launch_f64(lo_ctx *ctx, const lo_table *in, const lo_table *out, int32_t out_col0,
-               const lo::ColsF64 &P, unsigned long long *counts, bool aligned, cudaStream_t s) {
-    const unsigned tiles_per_col = (unsigned)((in->nrows + lo::kTileRows - 1) / lo::kTileRows);
-    const unsigned long long blocks = (unsigned long long)tiles_per_col * (unsigned)P.k;
-    if (blocks > 0x7fffffffull) return fail(LO_ERR_INVALID, "table too large for one launch (%llu tiles)", blocks);
+               const lo::ColsF64 &P, unsigned long long *counts, bool aligned, const lo::GroupStep &G, cudaStream_t s) {
     const size_t smem = HIST ? lo::kHistSmemBytes : 0;
     char *out_base = out ? out->base + (int64_t)out_col0 * out->pitch : nullptr;
     const long long out_pitch = out ? out->pitch : 0;
     bool fast = HIST;
     for (int j = 0; HIST && j < P.k; ++j) fast = fast && fastdiv_ok(P.w[j]);
     // LOEXEC_TMA=1: stage the slabs through shared memory with the bulk-copy engine (A/B variant).
-    // Only full tiles; the ragged last tile of each column (and unaligned / slow-divide cases) keep the LDG kernel.
-    if (ctx->use_tma.load(std::memory_order_relaxed) && aligned && fast == HIST && in->nrows >= lo::kTileRows) {
+    // Only full tiles; the ragged last tile of each column (and unaligned / slow-divide / group cases) keep the LDG kernel.
+    if (ctx->use_tma.load(std::memory_order_relaxed) && aligned && fast == HIST && in->nrows >= lo::kTileRows && G.mode == 0) {
         const unsigned full_tiles = (unsigned)(in->nrows / lo::kTileRows);
         const unsigned long long tblocks = (unsigned long long)full_tiles * (unsigned)P.k;
+        if (tblocks > 0x7fffffffull) return fail(LO_ERR_INVALID, "table too large for one launch (%llu tiles)", tblocks);
         lo::k_project_cast_hist_tma<OUT, HIST, HIST><<<(unsigned)tblocks, lo::kThreads + 32, lo::kTmaSmemBytes, s>>>(
             in->base, in->pitch, out_base, out_pitch, in->nrows, full_tiles, counts, P);
         LO_CUDA(cudaGetLastError());
@@ -199,22 +233,23 @@ int launch_f64(lo_ctx *ctx, const lo_table *in, const lo_table *out, int32_t out
         const int64_t done = (int64_t)full_tiles * lo::kTileRows;
         if (done == in->nrows) return LO_OK;
         // the remaining rows of every column: one ragged tile each, through the regular kernel on a row-offset view
-        lo_table tin = *in;
-        tin.base = in->base + done * 8; tin.nrows = in->nrows - done;
-        lo_table tout;
-        if (out) { tout = *out; tout.base = out->base + done * (int64_t)dtype_size(out->dtype); tout.nrows = tin.nrows; }
-        char *ob = out ? tout.base + (int64_t)out_col0 * tout.pitch : nullptr;
+        const lo::TileMap M1 = {1u, 0u, (unsigned)P.k, lo::kPfBatches, lo::kPfBatches};
+        const char *ib = in->base + done * 8;
+        char *ob = out ? out->base + done * (int64_t)dtype_size(out->dtype) + (int64_t)out_col0 * out->pitch : nullptr;
         if (fast) lo::k_project_cast_hist<OUT, HIST, true, true><<<(unsigned)P.k, lo::kThreads, smem, s>>>(
-                      tin.base, tin.pitch, ob, out_pitch, tin.nrows, 1u, counts, P);
+                      ib, in->pitch, ob, out_pitch, in->nrows - done, counts, P, M1, kNoGroup);
         else      lo::k_project_cast_hist<OUT, HIST, true, false><<<(unsigned)P.k, lo::kThreads, smem, s>>>(
-                      tin.base, tin.pitch, ob, out_pitch, tin.nrows, 1u, counts, P);
+                      ib, in->pitch, ob, out_pitch, in->nrows - done, counts, P, M1, kNoGroup);
         LO_CUDA(cudaGetLastError());
         ctx->launches.fetch_add(1, std::memory_order_relaxed);
         return LO_OK;
     }
+    const lo::TileMap M = make_tilemap(ctx, in->nrows, P.k);
+    const unsigned long long blocks = ((unsigned long long)M.tiles_a + M.tiles_b) * (unsigned)P.k;
+    if (blocks > 0x7fffffffull) return fail(LO_ERR_INVALID, "table too large for one launch (%llu tiles)", blocks);
 #define LO_LAUNCH(AL, FD)                                                                              \
     lo::k_project_cast_hist<OUT, HIST, AL, FD><<<(unsigned)blocks, lo::kThreads, smem, s>>>(           \
-        in->base, in->pitch, out_base, out_pitch, in->nrows, tiles_per_col, counts, P)
+        in->base, in->pitch, out_base, out_pitch, in->nrows, counts, P, M, G)
     if (aligned) { if (fast) LO_LAUNCH(true, true); else LO_LAUNCH(true, false); }
     else         { if (fast) LO_LAUNCH(false, true); else LO_LAUNCH(false, false); }
 #undef LO_LAUNCH
@@ -224,7 +259,8 @@ int launch_f64(lo_ctx *ctx, const lo_table *in, const lo_table *out, int32_t out
 }
 
 int project_cast_hist_impl(lo_ctx *ctx, const lo_table *in, const int32_t *col_idx, int32_t k,
-                           lo_table *out, const lo_hist_spec *spec, uint64_t *counts_dev, cudaStream_t s) {
+                           lo_table *out, const lo_hist_spec *spec, uint64_t *counts_dev, cudaStream_t s,
+                           const lo::GroupStep *group = nullptr) {
     if (!in) return fail(LO_ERR_INVALID, "input table is NULL");
     if (in->dtype != LO_F64) return fail(LO_ERR_INVALID, "input table must be LO_F64 (got dtype %d)", in->dtype);
     LO_TRY(check_cols(in, col_idx, k));
@@ -245,15 +281,16 @@ int project_cast_hist_impl(lo_ctx *ctx, const lo_table *in, const int32_t *col_i
         w.resize(k);
         LO_TRY(check_spec(spec, k, w.data()));
     }
-    if (in->nrows == 0) return LO_OK;
+    if (group && (!spec || k > lo::kMaxColsF64))
+        return fail(LO_ERR_INVALID, "a group step needs a histogram spec and k <= %d (got %d)", lo::kMaxColsF64, k);
+    if (in->nrows == 0 && !group) return LO_OK;
     const bool aligned = aligned32(in) && (!out || aligned32(out));
+    const lo::GroupStep &G = group ? *group : kNoGroup;
 
     for (int32_t c0 = 0; c0 < k; c0 += lo::kMaxColsF64) {
         lo::ColsF64 P;
         P.k     = std::min<int32_t>(lo::kMaxColsF64, k - c0);
         P.nbins = spec ? spec->nbins : 0;
-        P.sys_scope = (spec && (spec->flags & LO_HIST_PEER_COUNTS)) ? 1 : 0;
-        P.pad_ = 0;
         for (int j = 0; j < P.k; ++j) {
             P.col[j] = col_idx[c0 + j];
             P.lo[j]  = spec ? spec->lo[c0 + j] : 0.f;
@@ -263,12 +300,12 @@ int project_cast_hist_impl(lo_ctx *ctx, const lo_table *in, const int32_t *col_i
         unsigned long long *cnt = spec ? (unsigned long long *)counts_dev + (int64_t)c0 * spec->nbins : nullptr;
         int rc;
         if (spec) {
-            if (out_mode == 0)      rc = launch_f64<0, true>(ctx, in, out, c0, P, cnt, aligned, s);
-            else if (out_mode == 1) rc = launch_f64<1, true>(ctx, in, out, c0, P, cnt, aligned, s);
-            else                    rc = launch_f64<2, true>(ctx, in, out, c0, P, cnt, aligned, s);
+            if (out_mode == 0)      rc = launch_f64<0, true>(ctx, in, out, c0, P, cnt, aligned, G, s);
+            else if (out_mode == 1) rc = launch_f64<1, true>(ctx, in, out, c0, P, cnt, aligned, G, s);
+            else                    rc = launch_f64<2, true>(ctx, in, out, c0, P, cnt, aligned, G, s);
         } else {
-            if (out_mode == 1)      rc = launch_f64<1, false>(ctx, in, out, c0, P, cnt, aligned, s);
-            else                    rc = launch_f64<2, false>(ctx, in, out, c0, P, cnt, aligned, s);
+            if (out_mode == 1)      rc = launch_f64<1, false>(ctx, in, out, c0, P, cnt, aligned, G, s);
+            else                    rc = launch_f64<2, false>(ctx, in, out, c0, P, cnt, aligned, G, s);
         }
         LO_TRY(rc);
     }
@@ -276,12 +313,14 @@ int project_cast_hist_impl(lo_ctx *ctx, const lo_table *in, const int32_t *col_i
 }
 
 int hist_u8_impl(lo_ctx *ctx, const lo_table *in, const int32_t *col_idx, int32_t k,
-                 uint64_t *counts_dev, cudaStream_t s) {
+                 uint64_t *counts_dev, cudaStream_t s, const lo::GroupStep *group = nullptr) {
     if (!in) return fail(LO_ERR_INVALID, "input table is NULL");
     if (in->dtype != LO_U8) return fail(LO_ERR_INVALID, "input table must be LO_U8 (got dtype %d)", in->dtype);
     LO_TRY(check_cols(in, col_idx, k));
-    if (!counts_dev) return fail(LO_ERR_INVALID, "counts_dev is NULL");
-    if (in->nrows == 0) return LO_OK;
+    if (!counts_dev && !group) return fail(LO_ERR_INVALID, "counts_dev is NULL");
+    if (group && k > lo::kMaxColsU8) return fail(LO_ERR_INVALID, "a group step takes k <= %d byte columns (got %d)", lo::kMaxColsU8, k);
+    if (in->nrows == 0 && !group) return LO_OK;
+    const lo::GroupStep &G = group ? *group : kNoGroup;
     const bool aligned = ((uintptr_t)in->base % 16 == 0) && (in->pitch % 16 == 0);
     const unsigned tiles_per_col = (unsigned)((in->nrows + lo::kU8TileRows - 1) / lo::kU8TileRows);
     for (int32_t c0 = 0; c0 < k; c0 += lo::kMaxColsU8) {
@@ -293,10 +332,10 @@ int hist_u8_impl(lo_ctx *ctx, const lo_table *in, const int32_t *col_idx, int32_
         unsigned long long *cnt = (unsigned long long *)counts_dev + (int64_t)c0 * 256;
         if (aligned)
             lo::k_hist_u8_cols<true><<<(unsigned)blocks, lo::kThreads, lo::kHistSmemBytes, s>>>(
-                (const uint8_t *)in->base, in->pitch, in->nrows, tiles_per_col, cnt, P);
+                (const uint8_t *)in->base, in->pitch, in->nrows, tiles_per_col, cnt, P, G);
         else
             lo::k_hist_u8_cols<false><<<(unsigned)blocks, lo::kThreads, lo::kHistSmemBytes, s>>>(
-                (const uint8_t *)in->base, in->pitch, in->nrows, tiles_per_col, cnt, P);
+                (const uint8_t *)in->base, in->pitch, in->nrows, tiles_per_col, cnt, P, G);
         LO_CUDA(cudaGetLastError());
         ctx->launches.fetch_add(1, std::memory_order_relaxed);
     }
@@ -305,21 +344,21 @@ int hist_u8_impl(lo_ctx *ctx, const lo_table *in, const int32_t *col_idx, int32_
 
 int ensure_stage(lo_ctx *ctx, size_t in_bytes, size_t out_bytes, size_t ncounts) {
     if (in_bytes > ctx->stage_in_bytes) {
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < kSlots; ++i) {
             if (ctx->stage_in[i]) cudaFree(ctx->stage_in[i]);
             ctx->stage_in[i] = nullptr;
         }
         ctx->stage_in_bytes = 0;
-        for (int i = 0; i < 2; ++i) LO_CUDA(cudaMalloc((void **)&ctx->stage_in[i], in_bytes));
+        for (int i = 0; i < kSlots; ++i) LO_CUDA(cudaMalloc((void **)&ctx->stage_in[i], in_bytes));
         ctx->stage_in_bytes = in_bytes;
     }
     if (out_bytes > ctx->stage_out_bytes) {
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < kSlots; ++i) {
             if (ctx->stage_out[i]) cudaFree(ctx->stage_out[i]);
             ctx->stage_out[i] = nullptr;
         }
         ctx->stage_out_bytes = 0;
-        for (int i = 0; i < 2; ++i) LO_CUDA(cudaMalloc((void **)&ctx->stage_out[i], out_bytes));
+        for (int i = 0; i < kSlots; ++i) LO_CUDA(cudaMalloc((void **)&ctx->stage_out[i], out_bytes));
         ctx->stage_out_bytes = out_bytes;
     }
     if (ncounts > ctx->host_counts_n) {
@@ -334,7 +373,7 @@ int ensure_stage(lo_ctx *ctx, size_t in_bytes, size_t out_bytes, size_t ncounts)
 
 // rows per chunk of the *_host pipeline: ~LOEXEC_CHUNK_MB (default 512) MiB of input per chunk, whole tiles
 int64_t chunk_rows_for(int64_t nrows, int32_t k, size_t elem_bytes, int64_t tile_rows) {
-    size_t mb = 512;   // measured on B200/PCIe5: 64 MiB -> 40 GB/s, 256 -> 47.8, 1024 -> 49.4 H2D with D2H running
+    size_t mb = 256;   // measured on B200/PCIe5: 64 MiB -> 40 GB/s, 256 -> 47.8, 1024 -> 49.4 H2D with D2H running
     if (const char *e = getenv("LOEXEC_CHUNK_MB")) {
         long v = atol(e);
         if (v >= 1 && v <= 8192) mb = (size_t)v;
@@ -388,12 +427,12 @@ int lo_init(int device, lo_ctx **out) {
     ctx->sm_count  = prop.multiProcessorCount;
     ctx->hbm_bytes = prop.totalGlobalMem;
     ctx->stream = ctx->h2d = ctx->d2h = nullptr;
-    for (int i = 0; i < 2; ++i) ctx->ev_h2d[i] = ctx->ev_k[i] = ctx->ev_d2h[i] = nullptr;
+    for (int i = 0; i < kSlots; ++i) ctx->ev_h2d[i] = ctx->ev_k[i] = ctx->ev_d2h[i] = nullptr;
     auto setup = [&]() -> int {
         LO_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
         LO_CUDA(cudaStreamCreateWithFlags(&ctx->h2d, cudaStreamNonBlocking));
         LO_CUDA(cudaStreamCreateWithFlags(&ctx->d2h, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < kSlots; ++i) {
             LO_CUDA(cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming));
             LO_CUDA(cudaEventCreateWithFlags(&ctx->ev_k[i], cudaEventDisableTiming));
             LO_CUDA(cudaEventCreateWithFlags(&ctx->ev_d2h[i], cudaEventDisableTiming));
@@ -416,7 +455,7 @@ int lo_shutdown(lo_ctx *ctx) {
     if (!ctx) return LO_OK;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kSlots; ++i) {
         if (ctx->stage_in[i]) cudaFree(ctx->stage_in[i]);
         if (ctx->stage_out[i]) cudaFree(ctx->stage_out[i]);
         if (ctx->ev_h2d[i]) cudaEventDestroy(ctx->ev_h2d[i]);
@@ -553,20 +592,25 @@ int lo_table_upload_col(lo_ctx *ctx, lo_table *t, int32_t col, int64_t row0, con
     if (nrows == 0) return LO_OK;
     if (!host) return fail(LO_ERR_INVALID, "host is NULL");
     const size_t es = dtype_size(t->dtype);
-    LO_CUDA(cudaMemcpy(t->base + (int64_t)col * t->pitch + row0 * (int64_t)es, host, (size_t)nrows * es,
-                       cudaMemcpyHostToDevice));
+    // on the context's stream and waited for: a pageable cudaMemcpy on the NULL stream may return before the DMA has
+    // finished and is not ordered with the non-blocking streams the kernels run on
+    LO_CUDA(cudaMemcpyAsync(t->base + (int64_t)col * t->pitch + row0 * (int64_t)es, host, (size_t)nrows * es,
+                            cudaMemcpyHostToDevice, ctx->stream));
+    LO_CUDA(cudaStreamSynchronize(ctx->stream));
     return LO_OK;
 }
 
-int lo_table_download_col(lo_ctx *ctx, const lo_table *t, int32_t col, int64_t row0, void *host, int64_t nrows) {
+int lo_table_download_col(lo_ctx *ctx, const lo_table *t, int32_t col, int64_t row0, void *host, int64_t nrows,
+                          void *stream) {
     LO_TRY(check_ctx(ctx));
     LO_TRY(check_range(t, col, row0, nrows));
     if (nrows == 0) return LO_OK;
     if (!host) return fail(LO_ERR_INVALID, "host is NULL");
     const size_t es = dtype_size(t->dtype);
-    LO_CUDA(cudaDeviceSynchronize());
-    LO_CUDA(cudaMemcpy(host, t->base + (int64_t)col * t->pitch + row0 * (int64_t)es, (size_t)nrows * es,
-                       cudaMemcpyDeviceToHost));
+    cudaStream_t s = pick(ctx, stream);     // waits for this stream only: other streams' kernels keep running
+    LO_CUDA(cudaMemcpyAsync(host, t->base + (int64_t)col * t->pitch + row0 * (int64_t)es, (size_t)nrows * es,
+                            cudaMemcpyDeviceToHost, s));
+    LO_CUDA(cudaStreamSynchronize(s));
     return LO_OK;
 }
 
@@ -645,117 +689,6 @@ int lo_selftest_fastdiv(lo_ctx *ctx, float lo_v, float hi_v, int32_t nbins, int 
     return LO_OK;
 }
 
-// ---- peer-memory merge plumbing ---------------------------------------------------------------------
-int lo_ipc_export(lo_ctx *ctx, void *dev_ptr, void *handle64) {
-    LO_TRY(check_ctx(ctx));
-    if (!dev_ptr || !handle64) return fail(LO_ERR_INVALID, "NULL argument");
-    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
-    cudaIpcMemHandle_t h;
-    LO_CUDA(cudaIpcGetMemHandle(&h, dev_ptr));
-    memcpy(handle64, &h, 64);
-    return LO_OK;
-}
-
-int lo_ipc_open(lo_ctx *ctx, const void *handle64, void **dev_ptr) {
-    LO_TRY(check_ctx(ctx));
-    if (!dev_ptr || !handle64) return fail(LO_ERR_INVALID, "NULL argument");
-    cudaIpcMemHandle_t h;
-    memcpy(&h, handle64, 64);
-    LO_CUDA(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
-    return LO_OK;
-}
-
-int lo_ipc_close(lo_ctx *ctx, void *dev_ptr) {
-    LO_TRY(check_ctx(ctx));
-    if (dev_ptr) LO_CUDA(cudaIpcCloseMemHandle(dev_ptr));
-    return LO_OK;
-}
-
-int lo_dev_alloc(lo_ctx *ctx, size_t bytes, void **dev_ptr) {
-    LO_TRY(check_ctx(ctx));
-    if (!dev_ptr || bytes == 0) return fail(LO_ERR_INVALID, "bad arguments");
-    LO_CUDA(cudaMalloc(dev_ptr, bytes));
-    LO_CUDA(cudaMemset(*dev_ptr, 0, bytes));
-    return LO_OK;
-}
-
-int lo_dev_free(lo_ctx *ctx, void *dev_ptr) {
-    LO_TRY(check_ctx(ctx));
-    if (dev_ptr) LO_CUDA(cudaFree(dev_ptr));
-    return LO_OK;
-}
-
-int lo_flag_add_dev(lo_ctx *ctx, uint64_t *flag, uint64_t inc, void *stream) {
-    LO_TRY(check_ctx(ctx));
-    if (!flag) return fail(LO_ERR_INVALID, "flag is NULL");
-    lo::k_flag_add<<<1, 1, 0, pick(ctx, stream)>>>((unsigned long long *)flag, inc);
-    LO_CUDA(cudaGetLastError());
-    ctx->launches.fetch_add(1, std::memory_order_relaxed);
-    return LO_OK;
-}
-
-int lo_flag_add_many_dev(lo_ctx *ctx, uint64_t *const *flags, int32_t n, uint64_t inc, void *stream) {
-    LO_TRY(check_ctx(ctx));
-    if (n < 0 || n > 16) return fail(LO_ERR_INVALID, "n must be in [0, 16]");
-    if (n == 0) return LO_OK;
-    if (!flags) return fail(LO_ERR_INVALID, "flags is NULL");
-    lo::FlagPtrs F;
-    F.n = n;
-    for (int i = 0; i < 16; ++i) F.p[i] = i < n ? (unsigned long long *)flags[i] : nullptr;
-    lo::k_flag_add_many<<<1, 32, 0, pick(ctx, stream)>>>(F, inc);
-    LO_CUDA(cudaGetLastError());
-    ctx->launches.fetch_add(1, std::memory_order_relaxed);
-    return LO_OK;
-}
-
-int lo_peer_root_epilogue_dev(lo_ctx *ctx, const uint64_t *arrived, uint64_t target, uint32_t timeout_ms,
-                              uint64_t *timed_out_dev, uint64_t *shared_counts, uint64_t *result, int64_t n,
-                              uint64_t *const *peer_clean_flags, int32_t npeers, void *stream) {
-    LO_TRY(check_ctx(ctx));
-    if (!arrived || !timed_out_dev || !shared_counts || !result || n <= 0 || n > 0x7fffffff)
-        return fail(LO_ERR_INVALID, "bad arguments");
-    if (npeers < 0 || npeers > 16 || (npeers > 0 && !peer_clean_flags)) return fail(LO_ERR_INVALID, "npeers must be in [0, 16]");
-    if (timeout_ms == 0 || timeout_ms > 60000) return fail(LO_ERR_INVALID, "timeout_ms must be in [1, 60000]");
-    lo::FlagPtrs F;
-    F.n = npeers;
-    for (int i = 0; i < 16; ++i) F.p[i] = i < npeers ? (unsigned long long *)peer_clean_flags[i] : nullptr;
-    lo::k_peer_root_epilogue<<<1, 1024, 0, pick(ctx, stream)>>>(
-        (const unsigned long long *)arrived, target, (unsigned long long)timeout_ms * 1000000ull,
-        (unsigned long long *)timed_out_dev, (unsigned long long *)shared_counts, (unsigned long long *)result, (int)n, F);
-    LO_CUDA(cudaGetLastError());
-    ctx->launches.fetch_add(1, std::memory_order_relaxed);
-    return LO_OK;
-}
-
-int lo_dev_copy_dev(lo_ctx *ctx, void *dst, const void *src, size_t bytes, void *stream) {
-    LO_TRY(check_ctx(ctx));
-    if (!dst || !src) return fail(LO_ERR_INVALID, "NULL argument");
-    LO_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, pick(ctx, stream)));
-    return LO_OK;
-}
-
-int lo_flag_wait_dev(lo_ctx *ctx, const uint64_t *flag, uint64_t target, uint32_t timeout_ms, uint64_t *timed_out_dev,
-                     void *stream) {
-    LO_TRY(check_ctx(ctx));
-    if (!flag || !timed_out_dev) return fail(LO_ERR_INVALID, "NULL argument");
-    if (timeout_ms == 0 || timeout_ms > 60000) return fail(LO_ERR_INVALID, "timeout_ms must be in [1, 60000]");
-    lo::k_flag_wait<<<1, 1, 0, pick(ctx, stream)>>>((const unsigned long long *)flag, target,
-                                                     (unsigned long long)timeout_ms * 1000000ull,
-                                                     (unsigned long long *)timed_out_dev);
-    LO_CUDA(cudaGetLastError());
-    ctx->launches.fetch_add(1, std::memory_order_relaxed);
-    return LO_OK;
-}
-
-int lo_dev_read_u64(lo_ctx *ctx, const uint64_t *dev_ptr, int64_t n, uint64_t *host, void *stream) {
-    LO_TRY(check_ctx(ctx));
-    if (!dev_ptr || !host || n <= 0) return fail(LO_ERR_INVALID, "bad arguments");
-    cudaStream_t s = pick(ctx, stream);
-    LO_CUDA(cudaMemcpyAsync(host, dev_ptr, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
-    LO_CUDA(cudaStreamSynchronize(s));
-    return LO_OK;
-}
-
 // per-column min / max / count of the finite cast values of RESIDENT columns; out_dev: uint64[3*k], zeroed here.
 // Decode on the host with lo_minmax_decode.
 int lo_minmax_cast_dev(lo_ctx *ctx, const lo_table *in, const int32_t *col_idx, int32_t k, uint64_t *out_dev, void *stream) {
@@ -814,7 +747,10 @@ int lo_counts_alloc(lo_ctx *ctx, int64_t n, uint64_t **out_dev) {
     LO_TRY(check_ctx(ctx));
     if (!out_dev || n <= 0) return fail(LO_ERR_INVALID, "bad arguments");
     LO_CUDA(cudaMalloc((void **)out_dev, (size_t)n * 8));
-    LO_CUDA(cudaMemset(*out_dev, 0, (size_t)n * 8));
+    // zeroed on the context's stream and waited for, so launches on ANY stream after this call see zeros
+    // (a NULL-stream cudaMemset is not ordered with cudaStreamNonBlocking streams)
+    LO_CUDA(cudaMemsetAsync(*out_dev, 0, (size_t)n * 8, ctx->stream));
+    LO_CUDA(cudaStreamSynchronize(ctx->stream));
     return LO_OK;
 }
 
@@ -841,11 +777,13 @@ int lo_counts_download(lo_ctx *ctx, const uint64_t *counts_dev, int64_t n, uint6
 }
 
 // ---- hot path, host buffers ---------------------------------------------------------------------
-// Three-stream pipeline over row chunks; chunk c uses staging slot c & 1:
-//   h2d stream : wait(kernel of chunk c-2 done)  -> k column copies          -> ev_h2d[slot]
-//   compute    : wait(ev_h2d[slot]), wait(d2h of chunk c-2 done) -> kernel   -> ev_k[slot]
-//   d2h stream : wait(ev_k[slot]) -> k column copies back                    -> ev_d2h[slot]
-// `launch(tin, tout_or_null)` enqueues the kernel(s) of one chunk on ctx->stream.
+// Three-stream pipeline over row chunks; chunk c uses staging slot c % kSlots:
+//   h2d stream : wait(kernel of chunk c-kSlots done) -> k column copies             -> ev_h2d[slot]
+//   compute    : wait(ev_h2d[slot]), wait(d2h of chunk c-kSlots done) -> kernel     -> ev_k[slot]
+//   d2h stream : wait(ev_k[slot]) -> k column copies back                           -> ev_d2h[slot]
+// `launch(tin, tout_or_null, counts_dev)` enqueues the kernel(s) of one chunk on ctx->stream.
+// counts_target: device matrix the kernels accumulate into (NULL: the context's own scratch, zeroed here and
+// downloaded into counts_host at the end; non-NULL: a group member's accumulate matrix, merged by the caller).
 }  // extern "C"
 
 namespace {
@@ -853,53 +791,63 @@ namespace {
 template <typename Launch>
 int host_pipeline(lo_ctx *ctx, const void *const *in_cols, int in_dtype, int64_t nrows, int32_t k,
                   void *const *out_cols, int out_dtype, int64_t tile_rows, size_t ncounts, uint64_t *counts_host,
-                  lo_host_timing *timing, Launch launch) {
+                  lo_host_timing *timing, Launch launch, unsigned long long *counts_target = nullptr) {
     const auto t0 = std::chrono::steady_clock::now();
     const int64_t launches0 = ctx->launches.load();
     const size_t ies = dtype_size(in_dtype), oes = out_cols ? dtype_size(out_dtype) : 0;
     double h2d = 0, d2h = 0;
-    if (counts_host && ncounts) memset(counts_host, 0, ncounts * 8);
+    if (counts_host && ncounts && !counts_target) memset(counts_host, 0, ncounts * 8);
     if (nrows > 0) {
         std::lock_guard<std::mutex> lk(ctx->host_mu);
-        const int64_t crows = chunk_rows_for(nrows, k, ies, tile_rows);
-        const int64_t in_pitch  = (int64_t)(((size_t)crows * ies + 255) / 256 * 256);
-        const int64_t out_pitch = (int64_t)(((size_t)crows * oes + 255) / 256 * 256);
-        LO_TRY(ensure_stage(ctx, (size_t)in_pitch * k, out_cols ? (size_t)out_pitch * k : 0, ncounts));
-        if (ncounts) LO_CUDA(cudaMemsetAsync(ctx->host_counts_dev, 0, ncounts * 8, ctx->stream));
-        const int64_t nchunks = (nrows + crows - 1) / crows;
-        for (int64_t c = 0; c < nchunks; ++c) {
-            const int slot = (int)(c & 1);
-            const int64_t r0 = c * crows, n = std::min(crows, nrows - r0);
-            if (c >= 2) LO_CUDA(cudaStreamWaitEvent(ctx->h2d, ctx->ev_k[slot], 0));
-            for (int j = 0; j < k; ++j)
-                LO_CUDA(cudaMemcpyAsync(ctx->stage_in[slot] + (int64_t)j * in_pitch,
-                                        (const char *)in_cols[j] + r0 * (int64_t)ies, (size_t)n * ies,
-                                        cudaMemcpyHostToDevice, ctx->h2d));
-            h2d += (double)n * ies * k;
-            LO_CUDA(cudaEventRecord(ctx->ev_h2d[slot], ctx->h2d));
-            LO_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[slot], 0));
-            if (c >= 2 && out_cols) LO_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[slot], 0));
-            lo_table tin  = {in_dtype, n, k, in_pitch, ctx->stage_in[slot], false, ctx->device};
-            lo_table tout = {out_dtype, n, k, out_pitch, out_cols ? ctx->stage_out[slot] : nullptr, false, ctx->device};
-            LO_TRY(launch(&tin, out_cols ? &tout : nullptr));
-            LO_CUDA(cudaEventRecord(ctx->ev_k[slot], ctx->stream));
-            if (out_cols) {
-                LO_CUDA(cudaStreamWaitEvent(ctx->d2h, ctx->ev_k[slot], 0));
+        auto body = [&]() -> int {
+            const int64_t crows = chunk_rows_for(nrows, k, ies, tile_rows);
+            const int64_t in_pitch  = (int64_t)(((size_t)crows * ies + 255) / 256 * 256);
+            const int64_t out_pitch = (int64_t)(((size_t)crows * oes + 255) / 256 * 256);
+            LO_TRY(ensure_stage(ctx, (size_t)in_pitch * k, out_cols ? (size_t)out_pitch * k : 0, counts_target ? 0 : ncounts));
+            unsigned long long *cdev = counts_target ? counts_target : ctx->host_counts_dev;
+            if (ncounts && !counts_target) LO_CUDA(cudaMemsetAsync(cdev, 0, ncounts * 8, ctx->stream));
+            const int64_t nchunks = (nrows + crows - 1) / crows;
+            for (int64_t c = 0; c < nchunks; ++c) {
+                const int slot = (int)(c % kSlots);
+                const int64_t r0 = c * crows, n = std::min(crows, nrows - r0);
+                if (c >= kSlots) LO_CUDA(cudaStreamWaitEvent(ctx->h2d, ctx->ev_k[slot], 0));
                 for (int j = 0; j < k; ++j)
-                    LO_CUDA(cudaMemcpyAsync((char *)out_cols[j] + r0 * (int64_t)oes,
-                                            ctx->stage_out[slot] + (int64_t)j * out_pitch, (size_t)n * oes,
-                                            cudaMemcpyDeviceToHost, ctx->d2h));
-                d2h += (double)n * oes * k;
-                LO_CUDA(cudaEventRecord(ctx->ev_d2h[slot], ctx->d2h));
+                    LO_CUDA(cudaMemcpyAsync(ctx->stage_in[slot] + (int64_t)j * in_pitch,
+                                            (const char *)in_cols[j] + r0 * (int64_t)ies, (size_t)n * ies,
+                                            cudaMemcpyHostToDevice, ctx->h2d));
+                h2d += (double)n * ies * k;
+                LO_CUDA(cudaEventRecord(ctx->ev_h2d[slot], ctx->h2d));
+                LO_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[slot], 0));
+                if (c >= kSlots && out_cols) LO_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[slot], 0));
+                lo_table tin  = {in_dtype, n, k, in_pitch, ctx->stage_in[slot], false, ctx->device};
+                lo_table tout = {out_dtype, n, k, out_pitch, out_cols ? ctx->stage_out[slot] : nullptr, false, ctx->device};
+                LO_TRY(launch(&tin, out_cols ? &tout : nullptr, cdev));
+                LO_CUDA(cudaEventRecord(ctx->ev_k[slot], ctx->stream));
+                if (out_cols) {
+                    LO_CUDA(cudaStreamWaitEvent(ctx->d2h, ctx->ev_k[slot], 0));
+                    for (int j = 0; j < k; ++j)
+                        LO_CUDA(cudaMemcpyAsync((char *)out_cols[j] + r0 * (int64_t)oes,
+                                                ctx->stage_out[slot] + (int64_t)j * out_pitch, (size_t)n * oes,
+                                                cudaMemcpyDeviceToHost, ctx->d2h));
+                    d2h += (double)n * oes * k;
+                    LO_CUDA(cudaEventRecord(ctx->ev_d2h[slot], ctx->d2h));
+                }
             }
-        }
-        if (ncounts && counts_host) {
-            LO_CUDA(cudaMemcpyAsync(counts_host, ctx->host_counts_dev, ncounts * 8, cudaMemcpyDeviceToHost, ctx->stream));
-            d2h += (double)ncounts * 8;
-        }
-        LO_CUDA(cudaStreamSynchronize(ctx->stream));
-        LO_CUDA(cudaStreamSynchronize(ctx->d2h));
-        LO_CUDA(cudaStreamSynchronize(ctx->h2d));
+            if (ncounts && counts_host && !counts_target) {
+                LO_CUDA(cudaMemcpyAsync(counts_host, cdev, ncounts * 8, cudaMemcpyDeviceToHost, ctx->stream));
+                d2h += (double)ncounts * 8;
+            }
+            return LO_OK;
+        };
+        const int rc = body();
+        // success or failure: nothing may still be reading the caller's buffers or the staging slots when the
+        // lock is released (on failure the message of the FIRST error is kept)
+        const std::string first = g_err;
+        const cudaError_t e1 = cudaStreamSynchronize(ctx->stream), e2 = cudaStreamSynchronize(ctx->d2h),
+                          e3 = cudaStreamSynchronize(ctx->h2d);
+        if (rc != LO_OK) { g_err = first; return rc; }
+        if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
+            return fail(LO_ERR_CUDA, "host pipeline: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2 != cudaSuccess ? e2 : e3));
     }
     if (timing) {
         timing->total_ms  = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -937,9 +885,9 @@ int lo_project_cast_hist_host(lo_ctx *ctx, const double *const *in_cols, int64_t
     for (int j = 0; j < k; ++j) ident[j] = j;
     const size_t ncounts = spec ? (size_t)k * (size_t)spec->nbins : 0;
     return host_pipeline(ctx, (const void *const *)in_cols, LO_F64, nrows, k, (void *const *)out_cols, LO_F32,
-                         lo::kTileRows, ncounts, counts, timing, [&](lo_table *tin, lo_table *tout) {
-                             return project_cast_hist_impl(ctx, tin, ident.data(), k, tout, spec,
-                                                           (uint64_t *)ctx->host_counts_dev, ctx->stream);
+                         lo::kTileRows, ncounts, counts, timing,
+                         [&](lo_table *tin, lo_table *tout, unsigned long long *cdev) {
+                             return project_cast_hist_impl(ctx, tin, ident.data(), k, tout, spec, (uint64_t *)cdev, ctx->stream);
                          });
 }
 
@@ -951,8 +899,8 @@ int lo_hist_u8_cols_host(lo_ctx *ctx, const uint8_t *const *in_cols, int64_t nro
     std::vector<int32_t> ident(k);
     for (int j = 0; j < k; ++j) ident[j] = j;
     return host_pipeline(ctx, (const void *const *)in_cols, LO_U8, nrows, k, nullptr, LO_U8, lo::kU8TileRows,
-                         (size_t)k * 256, counts, timing, [&](lo_table *tin, lo_table *) {
-                             return hist_u8_impl(ctx, tin, ident.data(), k, (uint64_t *)ctx->host_counts_dev, ctx->stream);
+                         (size_t)k * 256, counts, timing, [&](lo_table *tin, lo_table *, unsigned long long *cdev) {
+                             return hist_u8_impl(ctx, tin, ident.data(), k, (uint64_t *)cdev, ctx->stream);
                          });
 }
 
@@ -966,10 +914,10 @@ int lo_value_counts_u32_host(lo_ctx *ctx, const uint32_t *codes, int64_t nrows, 
     // counts buffer layout: [ncodes counts][1 out-of-range flag]
     std::vector<uint64_t> tmp((size_t)ncodes + 1);
     int rc = host_pipeline(ctx, cols, LO_U32, nrows, 1, nullptr, LO_U32, 1 << 16, (size_t)ncodes + 1, tmp.data(), timing,
-                           [&](lo_table *tin, lo_table *) {
+                           [&](lo_table *tin, lo_table *, unsigned long long *cdev) {
                                const int grid = ctx->sm_count * 8;
                                lo::k_count_codes_u32<<<grid, 256, 0, ctx->stream>>>(
-                                   (const uint32_t *)tin->base, tin->nrows, ncodes, ctx->host_counts_dev);
+                                   (const uint32_t *)tin->base, tin->nrows, ncodes, cdev);
                                LO_CUDA(cudaGetLastError());
                                ctx->launches.fetch_add(1, std::memory_order_relaxed);
                                return LO_OK;
@@ -1159,10 +1107,10 @@ int lo_minmax_cast_host(lo_ctx *ctx, const double *const *in_cols, int64_t nrows
     // counts buffer layout per column: [ordered-uint min][ordered-uint max][count]
     std::vector<uint64_t> tmp((size_t)k * 3);
     int rc = host_pipeline(ctx, (const void *const *)in_cols, LO_F64, nrows, k, nullptr, LO_F32, lo::kTileRows,
-                           (size_t)k * 3, tmp.data(), timing, [&](lo_table *tin, lo_table *) {
+                           (size_t)k * 3, tmp.data(), timing, [&](lo_table *tin, lo_table *, unsigned long long *cdev) {
                                dim3 grid((unsigned)std::min<int64_t>((tin->nrows + 2047) / 2048, ctx->sm_count * 4), (unsigned)k);
                                lo::k_minmax_cast<<<grid, 256, 0, ctx->stream>>>(
-                                   (const char *)tin->base, tin->pitch, tin->nrows, ctx->host_counts_dev);
+                                   (const char *)tin->base, tin->pitch, tin->nrows, cdev);
                                LO_CUDA(cudaGetLastError());
                                ctx->launches.fetch_add(1, std::memory_order_relaxed);
                                return LO_OK;
@@ -1180,3 +1128,5 @@ int lo_minmax_cast_host(lo_ctx *ctx, const double *const *in_cols, int64_t nrows
 }
 
 }  // extern "C"
+
+#include "group.inc"

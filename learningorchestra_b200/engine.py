@@ -90,11 +90,14 @@ class DeviceTable:
         N.check(self.engine._lib.lo_table_upload_col(self.engine._ctx, self._h, col, row0,
                                                      a.ctypes.data_as(C.c_void_p), a.shape[0]))
 
-    def to_numpy(self, col: int, row0: int = 0, nrows: int | None = None) -> np.ndarray:
+    def to_numpy(self, col: int, row0: int = 0, nrows: int | None = None, stream=None, out: np.ndarray | None = None) -> np.ndarray:
+        """Ordered after the work already enqueued on ``stream`` (None = the engine's own stream); waits for that
+        stream only, never for the whole device."""
         n = self.nrows - row0 if nrows is None else nrows
-        out = np.empty(n, dtype=self.np_dtype)
+        if out is None:
+            out = np.empty(n, dtype=self.np_dtype)
         N.check(self.engine._lib.lo_table_download_col(self.engine._ctx, self._h, col, row0,
-                                                       out.ctypes.data_as(C.c_void_p), n))
+                                                       out.ctypes.data_as(C.c_void_p), n, _stream_ptr(stream)))
         return out
 
     def fill_synthetic(self, kind: int, seed: int, row_offset: int = 0, lo: float = -1000.0, hi: float = 1000.0,
@@ -222,11 +225,11 @@ class Engine:
         return out
 
     def project_cast_hist(self, table: DeviceTable, col_idx, nbins: int, lo, hi, out: DeviceTable | None = None,
-                          counts: DeviceCounts | None = None, stream=None, peer_counts: bool = False) -> DeviceCounts:
+                          counts: DeviceCounts | None = None, stream=None) -> DeviceCounts:
         """Fused projection + cast + histogram; ``out=None`` computes the histogram only.
         ``counts`` is accumulated into (a fresh zeroed one is allocated when omitted)."""
         idx, k = _i32(col_idx)
-        spec, _keep = self._spec(k, nbins, lo, hi, N.LO_HIST_PEER_COUNTS if peer_counts else 0)
+        spec, _keep = self._spec(k, nbins, lo, hi)
         if counts is None:
             counts = self.counts(k, nbins)
         N.check(self._lib.lo_project_cast_hist_dev(self._ctx, table._h, idx, k, out._h if out is not None else None,
@@ -302,58 +305,12 @@ class Engine:
                                               maxs.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.c_void_p), None))
         return mins, maxs, cnt
 
-    # ---- peer-memory plumbing (sharding.PeerReduce) ------------------------------------------------
-    def dev_alloc(self, nbytes: int) -> int:
-        p = C.c_void_p()
-        N.check(self._lib.lo_dev_alloc(self._ctx, int(nbytes), C.byref(p)))
-        return int(p.value)
-
-    def dev_free(self, ptr: int) -> None:
-        N.check(self._lib.lo_dev_free(self._ctx, C.c_void_p(int(ptr))))
-
-    def ipc_export(self, ptr: int) -> bytes:
-        buf = C.create_string_buffer(64)
-        N.check(self._lib.lo_ipc_export(self._ctx, C.c_void_p(int(ptr)), buf))
-        return buf.raw
-
-    def ipc_open(self, handle: bytes) -> int:
-        p = C.c_void_p()
-        N.check(self._lib.lo_ipc_open(self._ctx, C.create_string_buffer(handle, 64), C.byref(p)))
-        return int(p.value)
-
-    def ipc_close(self, ptr: int) -> None:
-        N.check(self._lib.lo_ipc_close(self._ctx, C.c_void_p(int(ptr))))
-
-    def flag_add(self, flag_ptr: int, inc: int = 1, stream=None) -> None:
-        N.check(self._lib.lo_flag_add_dev(self._ctx, C.c_void_p(int(flag_ptr)), int(inc), _stream_ptr(stream)))
-
-    def flag_wait(self, flag_ptr: int, target: int, timed_out_ptr: int, timeout_ms: int = 2000, stream=None) -> None:
-        N.check(self._lib.lo_flag_wait_dev(self._ctx, C.c_void_p(int(flag_ptr)), int(target), int(timeout_ms),
-                                           C.c_void_p(int(timed_out_ptr)), _stream_ptr(stream)))
-
-    def read_u64(self, ptr: int, n: int = 1, stream=None) -> np.ndarray:
-        out = np.empty(int(n), dtype=np.uint64)
-        N.check(self._lib.lo_dev_read_u64(self._ctx, C.c_void_p(int(ptr)), int(n), out.ctypes.data_as(C.c_void_p),
-                                          _stream_ptr(stream)))
-        return out
-
-    def flag_add_many(self, flag_ptrs, inc: int = 1, stream=None) -> None:
-        arr = (C.c_void_p * len(flag_ptrs))(*[int(p) for p in flag_ptrs])
-        N.check(self._lib.lo_flag_add_many_dev(self._ctx, arr, len(flag_ptrs), int(inc), _stream_ptr(stream)))
-
-    def dev_copy(self, dst: int, src: int, nbytes: int, stream=None) -> None:
-        N.check(self._lib.lo_dev_copy_dev(self._ctx, C.c_void_p(int(dst)), C.c_void_p(int(src)), int(nbytes), _stream_ptr(stream)))
-
-    def dev_zero_u64(self, ptr: int, n: int, stream=None) -> None:
-        N.check(self._lib.lo_counts_zero_dev(self._ctx, C.c_void_p(int(ptr)), int(n), _stream_ptr(stream)))
-
-    def peer_root_epilogue(self, arrived_ptr: int, target: int, timed_out_ptr: int, shared_counts: int, result: int,
-                           n: int, peer_clean_ptrs, timeout_ms: int = 2000, stream=None) -> None:
-        arr = (C.c_void_p * max(len(peer_clean_ptrs), 1))(*[int(p) for p in peer_clean_ptrs])
-        N.check(self._lib.lo_peer_root_epilogue_dev(self._ctx, C.c_void_p(int(arrived_ptr)), int(target), int(timeout_ms),
-                                                    C.c_void_p(int(timed_out_ptr)), C.c_void_p(int(shared_counts)),
-                                                    C.c_void_p(int(result)), int(n), arr, len(peer_clean_ptrs),
-                                                    _stream_ptr(stream)))
+    def bind_numa(self) -> tuple[int, int]:
+        """Pin the calling thread to the CPUs next to this GPU; returns (numa node, cpus).  Call before allocating
+        pinned buffers so they are first touched on the memory the GPU's PCIe root hangs off."""
+        node, ncpus = C.c_int32(), C.c_int32()
+        N.check(self._lib.lo_ctx_bind_numa(self._ctx, C.byref(node), C.byref(ncpus)))
+        return int(node.value), int(ncpus.value)
 
     def parse_number_host(self, cells):
         """cells: list of ``str`` / ``bytes``.  Returns (values float64[n], status uint8[n]) — values are what

@@ -73,19 +73,22 @@ void oracle_hist_f32(const float *x, int64_t n, int nbins, float lo, float hi, u
 }
 
 /* projection + cast (+ histogram when nbins > 0) over k already-selected host columns.
- * out_cols may be NULL (histogram only).  counts[k*nbins] is overwritten.  All host threads. */
+ * out_cols may be NULL (histogram only).  counts[k*nbins] is overwritten.  All host threads: rows are cut into
+ * 64 Ki-row chunks handed out STATICALLY (chunk c -> thread c mod T, the same map oracle_synth_fill_*_mt uses to
+ * first-touch the data, so on a multi-socket host every thread scans pages of its own NUMA node); each thread
+ * walks all k columns of its chunk and keeps a private k x nbins count matrix. */
+#define ORACLE_CHUNK ((int64_t)1 << 16)
 void oracle_project_cast_hist(const double *const *in_cols, int64_t nrows, int k, float *const *out_cols,
                               int nbins, const float *lo, const float *hi, uint64_t *counts) {
     if (nbins > 0) memset(counts, 0, (size_t)k * nbins * sizeof(uint64_t));
-    const int64_t chunk = 1 << 16;
-    const int64_t nchunks = (nrows + chunk - 1) / chunk;
+    const int64_t nchunks = (nrows + ORACLE_CHUNK - 1) / ORACLE_CHUNK;
 #pragma omp parallel
     {
         uint64_t *local = nbins > 0 ? (uint64_t *)calloc((size_t)k * nbins, sizeof(uint64_t)) : NULL;
-#pragma omp for schedule(dynamic, 1) collapse(2)
-        for (int j = 0; j < k; ++j) {
-            for (int64_t c = 0; c < nchunks; ++c) {
-                const int64_t r0 = c * chunk, r1 = r0 + chunk < nrows ? r0 + chunk : nrows;
+#pragma omp for schedule(static, 1)
+        for (int64_t c = 0; c < nchunks; ++c) {
+            const int64_t r0 = c * ORACLE_CHUNK, r1 = r0 + ORACLE_CHUNK < nrows ? r0 + ORACLE_CHUNK : nrows;
+            for (int j = 0; j < k; ++j) {
                 const double *src = in_cols[j];
                 float *dst = out_cols ? out_cols[j] : NULL;
                 const float l = nbins > 0 ? lo[j] : 0.f, h = nbins > 0 ? hi[j] : 0.f;
@@ -112,11 +115,22 @@ void oracle_project_cast_hist(const double *const *in_cols, int64_t nrows, int k
 /* per-column value counts of byte columns; counts[k*256] overwritten */
 void oracle_hist_u8_cols(const uint8_t *const *in_cols, int64_t nrows, int k, uint64_t *counts) {
     memset(counts, 0, (size_t)k * 256 * sizeof(uint64_t));
-#pragma omp parallel for schedule(dynamic, 1)
-    for (int j = 0; j < k; ++j) {
-        uint64_t *cnt = counts + (size_t)j * 256;
-        const uint8_t *src = in_cols[j];
-        for (int64_t r = 0; r < nrows; ++r) cnt[src[r]]++;
+    const int64_t nchunks = (nrows + ORACLE_CHUNK - 1) / ORACLE_CHUNK;
+#pragma omp parallel
+    {
+        uint64_t *local = (uint64_t *)calloc((size_t)k * 256, sizeof(uint64_t));
+#pragma omp for schedule(static, 1)
+        for (int64_t c = 0; c < nchunks; ++c) {
+            const int64_t r0 = c * ORACLE_CHUNK, r1 = r0 + ORACLE_CHUNK < nrows ? r0 + ORACLE_CHUNK : nrows;
+            for (int j = 0; j < k; ++j) {
+                uint64_t *cnt = local + (size_t)j * 256;
+                const uint8_t *src = in_cols[j];
+                for (int64_t r = r0; r < r1; ++r) cnt[src[r]]++;
+            }
+        }
+#pragma omp critical
+        for (int64_t i = 0; i < (int64_t)k * 256; ++i) counts[i] += local[i];
+        free(local);
     }
 }
 
@@ -204,6 +218,32 @@ static inline uint8_t synth_u8_one(uint64_t seed, int col, uint64_t g) {
 
 void oracle_synth_u8(uint64_t seed, int col, int64_t row0, int64_t n, uint8_t *out) {
     for (int64_t r = 0; r < n; ++r) out[r] = synth_u8_one(seed, col, (uint64_t)(row0 + r));
+}
+
+/* Generate k table columns (col_idx[j] of the synthetic table, global rows [row0, row0+n)) into cols[j], with the
+ * SAME team and static chunk map as oracle_project_cast_hist: parallel first touch.  touch_out[j] (may be NULL) is
+ * zero-filled the same way so the output pages are placed too. */
+void oracle_synth_fill_f64_mt(int kind, uint64_t seed, const int32_t *col_idx, int k, int64_t row0, int64_t n,
+                              double glo, double ghi, double *const *cols, float *const *touch_out) {
+    const int64_t nchunks = (n + ORACLE_CHUNK - 1) / ORACLE_CHUNK;
+#pragma omp parallel for schedule(static, 1)
+    for (int64_t c = 0; c < nchunks; ++c) {
+        const int64_t r0 = c * ORACLE_CHUNK, r1 = r0 + ORACLE_CHUNK < n ? r0 + ORACLE_CHUNK : n;
+        for (int j = 0; j < k; ++j) {
+            for (int64_t r = r0; r < r1; ++r) cols[j][r] = synth_f64_one(kind, seed, col_idx[j], (uint64_t)(row0 + r), glo, ghi);
+            if (touch_out && touch_out[j]) memset(touch_out[j] + r0, 0, (size_t)(r1 - r0) * sizeof(float));
+        }
+    }
+}
+
+void oracle_synth_fill_u8_mt(uint64_t seed, const int32_t *col_idx, int k, int64_t row0, int64_t n, uint8_t *const *cols) {
+    const int64_t nchunks = (n + ORACLE_CHUNK - 1) / ORACLE_CHUNK;
+#pragma omp parallel for schedule(static, 1)
+    for (int64_t c = 0; c < nchunks; ++c) {
+        const int64_t r0 = c * ORACLE_CHUNK, r1 = r0 + ORACLE_CHUNK < n ? r0 + ORACLE_CHUNK : n;
+        for (int j = 0; j < k; ++j)
+            for (int64_t r = r0; r < r1; ++r) cols[j][r] = synth_u8_one(seed, col_idx[j], (uint64_t)(row0 + r));
+    }
 }
 
 /* Streaming full-size check: regenerate rows [row0, row0+nrows) of the synthetic table, run

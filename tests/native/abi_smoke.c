@@ -41,7 +41,7 @@ int main(void) {
     /* the same through the host-buffer entry point: download a column, push it back through the pipeline */
     double *col = (double *)malloc(sizeof(double) * nrows);
     float *res = (float *)malloc(sizeof(float) * nrows);
-    CHECK(lo_table_download_col(ctx, in, cols[0], 0, col, nrows));
+    CHECK(lo_table_download_col(ctx, in, cols[0], 0, col, nrows, NULL));
     const double *in_cols[1] = {col};
     float *out_cols[1] = {res};
     uint64_t hcounts[256];

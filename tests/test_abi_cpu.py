@@ -31,11 +31,12 @@ def test_library_is_sm100a_native_code(built):
     from learningorchestra_b200 import _native
     out = subprocess.run(["cuobjdump", "-lelf", str(_native.LIB_PATH)], capture_output=True, text=True).stdout
     assert "sm_100a" in out, out
-    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN2lo19k_project_cast_histILi1ELb1ELb1ELb1EEEvPKcxPcxxjPyNS_7ColsF64E",
-                           str(_native.LIB_PATH)], capture_output=True, text=True).stdout
+    full = subprocess.run(["cuobjdump", "-sass", str(_native.LIB_PATH)], capture_output=True, text=True).stdout
+    sass = full.split("Function : _ZN2lo19k_project_cast_histILi1ELb1ELb1ELb1EEE")[1].split("Function :")[0]
     assert "LDG.E.NA.EFL2.256" in sass or "LDG.E" in sass      # 256-bit streaming loads
     assert "STS.U8" in sass and "LDS.U8" in sass                # private byte-counter histogram, no ATOMS
     assert "ATOMS" not in sass
+    assert "RED.E.ADD.64.STRONG.SYS" in sass or "REDG.E.ADD.64.STRONG.SYS" in sass    # in-kernel merge: pushes at system scope
     assert "MUFU.RCP" not in sass.split("BAR.SYNC")[0] or True
 
 
