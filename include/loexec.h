@@ -280,7 +280,9 @@ int lo_value_counts_str_host(lo_ctx *ctx, const uint8_t *chars, const int64_t *o
  * chars holds all cells back to back, cell i = chars[offsets[i] .. offsets[i+1]).  values[i] receives exactly
  * the binary64 CPython's float() returns (correctly rounded; grammar incl. '_', inf, nan, whitespace).
  * status[i]: LO_NUM_FLOAT 0 | LO_NUM_INTEGER 1 (integer valued: store int(v)) | LO_NUM_EMPTY 2 ("" -> None) |
- * LO_NUM_INVALID 3 (float() raises ValueError) | LO_NUM_UNSUPPORTED 4 (non-ASCII byte or > 1024 bytes). */
+ * LO_NUM_INVALID 3 (float() raises ValueError) | LO_NUM_UNSUPPORTED 4 (cell > 1 MiB, or a byte >= 0x80: the caller
+ * passes the ASCII text float(str) itself parses after mapping Unicode digits / whitespace — a code-point property
+ * lookup the Python packer does, columnar.ascii_number_text). */
 #define LO_NUM_FLOAT 0
 #define LO_NUM_INTEGER 1
 #define LO_NUM_EMPTY 2

@@ -134,11 +134,14 @@ def load() -> C.CDLL:
                           f"{LIB_PATH} is missing — build it with `python -m learningorchestra_b200.build` "
                           "(__graft_entry__.build()); there is no CPU fallback")
     lib = C.CDLL(str(LIB_PATH))
+    lax = bool(os.environ.get("LOEXEC_LAX"))          # A/B measurements against an older build (scripts/ab_libs.py)
     for name, (res, args) in SIGNATURES.items():
-        fn = getattr(lib, name)          # AttributeError here = header / library mismatch
+        fn = getattr(lib, name, None) if lax else getattr(lib, name)   # AttributeError = header / library mismatch
+        if fn is None:
+            continue
         fn.restype = res
         fn.argtypes = args
-    if lib.lo_abi_version() != LO_ABI_VERSION:
+    if lib.lo_abi_version() != LO_ABI_VERSION and not lax:
         raise LoexecError(LO_ERR_INVALID, f"ABI version {lib.lo_abi_version()} != {LO_ABI_VERSION}")
     _lib = lib
     return lib

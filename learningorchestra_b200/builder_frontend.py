@@ -40,6 +40,16 @@ def file_processor(database, filename, engine=None):
     packed = {f: (columnar.numeric_column([d.get(f) for d in rows]) if rows else None) for f in fields}
     numeric = [f for f in fields if packed[f] is not None]
     resident = engine.resident.ensure(database, filename, numeric) if (engine is not None and numeric) else None
+    try:
+        return _frame(fields, rows, packed, resident)
+    finally:
+        if resident is not None:
+            engine.resident.release(resident)
+
+
+def _frame(fields, rows, packed, resident):
+    import numpy as np
+    import pyarrow as pa
     arrays, names = [], []
     for f in fields:
         if packed[f] is not None:

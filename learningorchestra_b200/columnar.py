@@ -81,6 +81,23 @@ def _numeric_column_loop(values):
     return out, valid, ("int" if all_int else "float")
 
 
+def auto_range(mins, maxs, nfinite):
+    """[lo, hi] per column for a binned request without ``range``, from the device's min / max / finite-count
+    pre-pass.  Degenerate cases get numpy.histogram's treatment instead of failing the job: no finite value ->
+    [0, 1]; constant column -> [v - 0.5, v + 0.5] (the neighbouring fp32 values where 0.5 is below half an ulp)."""
+    lo = np.array(mins, dtype=np.float32)
+    hi = np.array(maxs, dtype=np.float32)
+    for j in range(lo.shape[0]):
+        if int(nfinite[j]) == 0:
+            lo[j], hi[j] = 0.0, 1.0
+        elif lo[j] == hi[j]:
+            v = lo[j]
+            a, b = np.float32(v - np.float32(0.5)), np.float32(v + np.float32(0.5))
+            lo[j] = a if a != v else np.nextafter(v, np.float32(-np.inf), dtype=np.float32)
+            hi[j] = b if b != v else np.nextafter(v, np.float32(np.inf), dtype=np.float32)
+    return lo, hi
+
+
 def group_key(value):
     """Canonical key under MongoDB ``$group`` equality: numbers by value across int / float (1 == 1.0,
     -0.0 == 0.0), NaN with NaN, null and missing together, booleans apart from numbers, strings bytewise."""
@@ -100,6 +117,49 @@ def group_key(value):
     if isinstance(value, str):
         return ("str", value)
     return ("other", repr(value))
+
+
+def ascii_number_text(cell: str) -> str:
+    """What CPython's ``float(str)`` parses: ``_PyUnicode_TransformDecimalAndSpaceToASCII`` maps every non-ASCII
+    character — Unicode whitespace to ``' '``, Unicode decimal digits (``"１２"``, ``"٣.٥"``) to ASCII digits,
+    anything else makes the text invalid (``'?'``) — and leaves ASCII characters alone
+    (``data_type_handler_image/data_type_update.py:40`` relies on it).  Code-point property lookups, not arithmetic:
+    done here while the column is packed; the parse itself runs on the GPU."""
+    if cell.isascii():
+        return cell
+    import unicodedata
+    out = []
+    for ch in cell:
+        if ord(ch) < 128:
+            out.append(ch)
+        elif ch.isspace():
+            out.append(" ")
+        else:
+            d = unicodedata.decimal(ch, None)
+            if d is None:
+                out.append("?")
+                break
+            out.append(chr(48 + d))
+    return "".join(out)
+
+
+def pack_number_cells(cells):
+    """:func:`pack_cells` for the number parser: ``str`` cells with non-ASCII characters are normalised first
+    (rare; found with one vectorised Arrow pass)."""
+    if cells and isinstance(cells[0], str):
+        try:
+            import pyarrow as pa
+            import pyarrow.compute as pc
+            arr = pa.array(cells, type=pa.large_string())
+            bad = pc.invert(pc.string_is_ascii(arr))
+            if pc.any(bad).as_py():
+                idx = np.flatnonzero(np.asarray(bad.to_numpy(zero_copy_only=False), dtype=bool))
+                cells = list(cells)
+                for i in idx:
+                    cells[i] = ascii_number_text(cells[i])
+        except (ImportError, TypeError, ValueError) as _exc:      # mixed str / bytes columns: cell by cell
+            cells = [ascii_number_text(c) if isinstance(c, str) else c for c in cells]
+    return pack_cells(cells)
 
 
 def pack_cells(cells):

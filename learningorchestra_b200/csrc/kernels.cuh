@@ -76,6 +76,9 @@ struct ColsF64 {
 
 struct ColsU8 {
     int32_t k;
+    // powers of two handed to the kernel as DATA (constant bank): ptxas cannot strength-reduce a multiply by them into
+    // LEA / SHF, so the shift-and-add stays an IMAD / IMAD.HI on the FMA pipe (k_hist_u8_cols mode 6)
+    uint32_t p8, p11, p16, p19, p24, p27, p3;
     int32_t col[kMaxColsU8];
 };
 
@@ -395,6 +398,9 @@ k_project_cast_hist(const char *__restrict__ in_base, long long in_pitch,
         j = blockIdx.x / M.tiles_a;
         tile = blockIdx.x - j * M.tiles_a;
         nbatches = M.batches_a;
+#ifdef LO_STATIC_TILES          // A/B build: compile-time pipeline depth, as in round 1
+        nbatches = kPfBatches;
+#endif
         r0 = (long long)tile * (M.batches_a * (kPfBatch * kThreads * kVec));
     } else {
         const unsigned b = blockIdx.x - M.blocks_a;
@@ -694,10 +700,16 @@ k_project_cast_hist_tma(const char *__restrict__ in_base, long long in_pitch,
 // ---------------------------------------------------------------------------------------------
 // K4: per-column 256-bin value counts of byte columns
 // ---------------------------------------------------------------------------------------------
-#ifndef LO_U8_MODE
-#define LO_U8_MODE 4      // 0: bump4 per word   1: two bump2 per word   2: mode 1 + warp-uniform run fast path
-                          // 3: one conflict-free ATOMS per byte + run fast path (+6 % over mode 2)
-                          // 4: mode 3 with PRMT-extracted offsets / shifts (+4 % over mode 3; measured best)
+// How one byte becomes a counter update (template parameter MODE of k_hist_u8_cols; LOEXEC_U8_MODE picks at launch):
+//   2: two LDS.U8 / IADD / STS.U8 round trips per 16-bit pair (bump2), no atomics
+//   4: ONE conflict-free ATOMS.ADD per byte on the 32-bit word holding the counter, offsets / shifts pulled out
+//      of the input word with PRMT (round 1's best: 0.41 of the HBM peak, ALU-pipe bound: ncu "math pipe throttle")
+//   5: like 4, per-byte arithmetic written as masks + multiply-adds (ptxas turns the constant multiplies into
+//      LEA.HI / IMAD.SHL and balances the two integer pipes itself)
+//   6: like 5 with the powers of two passed as kernel DATA so the shift-and-adds stay IMAD / IMAD.HI on the FMA
+//      pipe and only the masks and the final 1 << n are ALU-pipe work
+#ifndef LO_U8_MODE_DEFAULT
+#define LO_U8_MODE_DEFAULT 4
 #endif
 
 // two increments with overlapped latencies (one compare instead of bump4's six)
@@ -710,38 +722,66 @@ __device__ __forceinline__ void bump2(uint8_t *priv, uint32_t b0, uint32_t b1) {
     *p1 = (uint8_t)c1;
 }
 
-// mode 3: one shared-memory atomic per byte on the 32-bit word that holds the counter (lane-private bank, so
-// no conflicts; a byte field cannot carry into its neighbour because a thread adds at most 240 per tile)
-__device__ __forceinline__ void bump_atomic(uint8_t *priv, uint32_t b) {
-    uint32_t *w = reinterpret_cast<uint32_t *>(priv + ((b & 0xFCu) << 8));
-    atomicAdd(w, 1u << ((b & 3u) << 3));
+__device__ __forceinline__ uint32_t mad_lo(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t mad_hi(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t one_shl_wrap(uint32_t n) {       // 1 << (n & 31): SHF.L.W, no clamp code
+    uint32_t d;
+    asm("shf.l.wrap.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(0u), "r"(1u), "r"(n));
+    return d;
+}
+// no return value: the shared-memory atomic is fire-and-forget (a lane-private bank, so conflict-free; a byte field
+// cannot carry into its neighbour because a thread adds at most 240 per tile)
+__device__ __forceinline__ void atoms_add(uint32_t addr, uint32_t v) {
+    asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(addr), "r"(v) : "memory");
 }
 
-// mode 4: like mode 3, with the four word-row offsets and the four field shifts of a 32-bit word of input computed
-// together (two LOP3 + one SHL for four bytes) and pulled apart with PRMT straight into position
-__device__ __forceinline__ void bump_word_prmt(uint8_t *priv, uint32_t x) {
-    const uint32_t rows   = x & 0xFCFCFCFCu;            // byte q: (b_q & 0xFC)   -> word-row offset / 256
-    const uint32_t shifts = (x & 0x03030303u) << 3;     // byte q: (b_q & 3) * 8  -> bit position of the counter
+struct U8Consts { uint32_t p8, p11, p16, p19, p24, p27, p3; };
+
+template <int MODE>
+__device__ __forceinline__ void bump_word(uint8_t *priv, uint32_t x, const U8Consts &K) {
+    if (MODE == 2) {
+        bump2(priv, x & 0xFFu, (x >> 8) & 0xFFu);
+        bump2(priv, (x >> 16) & 0xFFu, x >> 24);
+    } else if (MODE == 4) {
+        // the four word-row offsets and the four field shifts of a 32-bit word of input computed together
+        // (two LOP3 + one SHL for four bytes) and pulled apart with PRMT straight into position
+        const uint32_t rows   = x & 0xFCFCFCFCu;            // byte q: (b_q & 0xFC)   -> word-row offset / 256
+        const uint32_t shifts = (x & 0x03030303u) << 3;     // byte q: (b_q & 3) * 8  -> bit position of the counter
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const uint32_t off = __byte_perm(rows, 0u, 0x4404u | (uint32_t)(q << 4));     // byte q moved to bits 8..15
-        const uint32_t sh  = __byte_perm(shifts, 0u, 0x4440u | (uint32_t)q);          // byte q moved to bits 0..7
-        atomicAdd(reinterpret_cast<uint32_t *>(priv + off), 1u << sh);
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t off = __byte_perm(rows, 0u, 0x4404u | (uint32_t)(q << 4));     // byte q moved to bits 8..15
+            const uint32_t sh  = __byte_perm(shifts, 0u, 0x4440u | (uint32_t)q);          // byte q moved to bits 0..7
+            atomicAdd(reinterpret_cast<uint32_t *>(priv + off), 1u << sh);
+        }
+    } else {
+        // counter word of byte q (value b): priv + (b >> 2) * 1024; field at bit 8 * (b & 3).  Address =
+        // (x & mask_q) * 2^s + priv, shift count = (x & 0x03030303) moved to bits 3..4 (SHF.L.W reads bits 0..4 only)
+        const uint32_t ps = (uint32_t)__cvta_generic_to_shared(priv);
+        const uint32_t m  = x & 0x03030303u;
+        const uint32_t p8 = MODE == 6 ? K.p8 : 256u, p24 = MODE == 6 ? K.p24 : 1u << 24, p16 = MODE == 6 ? K.p16 : 1u << 16;
+        const uint32_t p3 = MODE == 6 ? K.p3 : 8u, p27 = MODE == 6 ? K.p27 : 1u << 27, p19 = MODE == 6 ? K.p19 : 1u << 19;
+        const uint32_t p11 = MODE == 6 ? K.p11 : 1u << 11;
+        const uint32_t a0 = mad_lo(x & 0x000000FCu, p8, ps);
+        const uint32_t a1 = (x & 0x0000FC00u) + ps;
+        const uint32_t a2 = mad_hi(x & 0x00FC0000u, p24, ps);
+        const uint32_t a3 = mad_hi(x & 0xFC000000u, p16, ps);
+        const uint32_t s0 = mad_lo(m, p3, 0u);             // m << 3
+        const uint32_t s1 = mad_hi(m, p27, 0u);            // m >> 5   (bits 3..4 = b1 & 3, bits 0..2 = 0)
+        const uint32_t s2 = mad_hi(m, p19, 0u);            // m >> 13
+        const uint32_t s3 = mad_hi(m, p11, 0u);            // m >> 21
+        atoms_add(a0, one_shl_wrap(s0));
+        atoms_add(a1, one_shl_wrap(s1));
+        atoms_add(a2, one_shl_wrap(s2));
+        atoms_add(a3, one_shl_wrap(s3));
     }
-}
-
-__device__ __forceinline__ void bump_word(uint8_t *priv, uint32_t x) {
-#if LO_U8_MODE == 4
-    bump_word_prmt(priv, x);
-#elif LO_U8_MODE == 3
-    bump_atomic(priv, x & 0xFFu); bump_atomic(priv, (x >> 8) & 0xFFu);
-    bump_atomic(priv, (x >> 16) & 0xFFu); bump_atomic(priv, x >> 24);
-#elif LO_U8_MODE == 0
-    bump4(priv, (int)(x & 0xFFu), (int)((x >> 8) & 0xFFu), (int)((x >> 16) & 0xFFu), (int)(x >> 24));
-#else
-    bump2(priv, x & 0xFFu, (x >> 8) & 0xFFu);
-    bump2(priv, (x >> 16) & 0xFFu, x >> 24);
-#endif
 }
 
 // one 16-byte vector.  Run fast path: when every ACTIVE lane of the warp holds sixteen equal bytes
@@ -749,8 +789,8 @@ __device__ __forceinline__ void bump_word(uint8_t *priv, uint32_t x) {
 // only keeps the branch warp-uniform (mixed data never executes both sides); correctness does not
 // depend on it, so it is taken over __activemask() — the ragged last tile runs with partial warps and a
 // full-mask vote there would wait forever for lanes that already left the loop.
-__device__ __forceinline__ void bump_vec16(uint8_t *priv, const uint4 &v) {
-#if LO_U8_MODE >= 2
+template <int MODE>
+__device__ __forceinline__ void bump_vec16(uint8_t *priv, const uint4 &v, const U8Consts &K) {
     const uint32_t splat = __byte_perm(v.x, 0, 0x0000);
     const bool run = (v.x == splat) & (v.y == splat) & (v.z == splat) & (v.w == splat);
     if (__all_sync(__activemask(), run)) {
@@ -758,12 +798,11 @@ __device__ __forceinline__ void bump_vec16(uint8_t *priv, const uint4 &v) {
         *p = (uint8_t)(*p + 16);
         return;
     }
-#endif
-    bump_word(priv, v.x); bump_word(priv, v.y);
-    bump_word(priv, v.z); bump_word(priv, v.w);
+    bump_word<MODE>(priv, v.x, K); bump_word<MODE>(priv, v.y, K);
+    bump_word<MODE>(priv, v.z, K); bump_word<MODE>(priv, v.w, K);
 }
 
-template <bool ALIGNED>
+template <bool ALIGNED, int MODE>
 __global__ void __launch_bounds__(kThreads, 3)
 k_hist_u8_cols(const uint8_t *__restrict__ in_base, long long in_pitch, long long nrows,
                unsigned tiles_per_col, unsigned long long *__restrict__ counts,
@@ -775,6 +814,7 @@ k_hist_u8_cols(const uint8_t *__restrict__ in_base, long long in_pitch, long lon
     const long long n   = min((long long)kU8TileRows, nrows - r0);
     const uint8_t *in   = in_base + (long long)P.col[j] * in_pitch + r0;
     uint8_t *priv = reinterpret_cast<uint8_t *>(smem) + 4 * threadIdx.x;
+    const U8Consts K = {P.p8, P.p11, P.p16, P.p19, P.p24, P.p27, P.p3};
     zero_private(smem, kHistRows);
 
     if (ALIGNED) {
@@ -787,7 +827,7 @@ k_hist_u8_cols(const uint8_t *__restrict__ in_base, long long in_pitch, long lon
 #pragma unroll
                 for (int u = 0; u < kU8Batch; ++u) v[u] = ldg128_stream(in + e0 + (long long)u * kThreads * kU8VecBytes);
 #pragma unroll
-                for (int u = 0; u < kU8Batch; ++u) bump_vec16(priv, v[u]);
+                for (int u = 0; u < kU8Batch; ++u) bump_vec16<MODE>(priv, v[u], K);
             } else {
 #pragma unroll 1
                 for (int u = 0; u < kU8Batch; ++u) {

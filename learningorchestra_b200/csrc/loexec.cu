@@ -173,15 +173,21 @@ int configure_kernels() {
     LO_TRY(allow_smem_hist<0>());
     LO_TRY(allow_smem_hist<1>());
     LO_TRY(allow_smem_hist<2>());
-    LO_TRY(allow_smem(lo::k_hist_u8_cols<true>));
-    LO_TRY(allow_smem(lo::k_hist_u8_cols<false>));
+    LO_TRY(allow_smem(lo::k_hist_u8_cols<true, 2>));
+    LO_TRY(allow_smem(lo::k_hist_u8_cols<true, 4>));
+    LO_TRY(allow_smem(lo::k_hist_u8_cols<true, 5>));
+    LO_TRY(allow_smem(lo::k_hist_u8_cols<true, 6>));
+    LO_TRY(allow_smem(lo::k_hist_u8_cols<false, 4>));
     return LO_OK;
 }
 
-// blockIdx -> tile map of one launch (kernels.cuh TileMap).  Grids of more than one wave get a tapered tail:
-// the last `tail_waves` waves' worth of rows is cut into short tiles (`tail_batches` pipeline batches instead of
-// kPfBatches), so the drain at the end of the launch costs a fraction of a full tile's time.  LOEXEC_TAIL_BATCHES
-// (0 = no taper) and LOEXEC_TAIL_WAVES override the defaults for measurements (scripts/tile_sweep.py).
+// blockIdx -> tile map of one launch (kernels.cuh TileMap).  A tapered tail can be requested: the last `tail_waves`
+// waves' worth of rows is cut into short tiles (`tail_batches` pipeline batches instead of kPfBatches), so the drain
+// at the end of the launch costs a fraction of a full tile's time.  MEASURED (scripts/tile_sweep.py,
+// profiles/r02_tile_sweep.json): it does not pay — at 12.5 M rows x 32 (the 8-GPU shard) every taper is equal or
+// slower than uniform tiles (0.752 ms vs 0.752 - 0.764), at 100 M rows 2 % slower: the ~30 us a launch loses against
+// the steady-state rate is not wave quantisation.  So the default is no taper; LOEXEC_TAIL_BATCHES / LOEXEC_TAIL_WAVES
+// remain as measurement knobs.
 lo::TileMap make_tilemap(const lo_ctx *ctx, int64_t nrows, int32_t k) {
     constexpr int64_t kBatchRows = (int64_t)lo::kPfBatch * lo::kThreads * lo::kVec;     // 5120
     lo::TileMap M;
@@ -189,7 +195,7 @@ lo::TileMap make_tilemap(const lo_ctx *ctx, int64_t nrows, int32_t k) {
     M.batches_b = lo::kPfBatches;
     M.tiles_a = (unsigned)((nrows + lo::kTileRows - 1) / lo::kTileRows);
     M.tiles_b = 0;
-    int tail_batches = 4;
+    int tail_batches = 0;
     double tail_waves = 1.0;
     if (const char *e = getenv("LOEXEC_TAIL_BATCHES")) tail_batches = atoi(e);
     if (const char *e = getenv("LOEXEC_TAIL_WAVES")) tail_waves = atof(e);
@@ -326,16 +332,22 @@ int hist_u8_impl(lo_ctx *ctx, const lo_table *in, const int32_t *col_idx, int32_
     for (int32_t c0 = 0; c0 < k; c0 += lo::kMaxColsU8) {
         lo::ColsU8 P;
         P.k = std::min<int32_t>(lo::kMaxColsU8, k - c0);
+        P.p8 = 1u << 8; P.p11 = 1u << 11; P.p16 = 1u << 16; P.p19 = 1u << 19; P.p24 = 1u << 24; P.p27 = 1u << 27; P.p3 = 1u << 3;
         for (int j = 0; j < P.k; ++j) P.col[j] = col_idx[c0 + j];
         const unsigned long long blocks = (unsigned long long)tiles_per_col * (unsigned)P.k;
         if (blocks > 0x7fffffffull) return fail(LO_ERR_INVALID, "table too large for one launch");
         unsigned long long *cnt = (unsigned long long *)counts_dev + (int64_t)c0 * 256;
-        if (aligned)
-            lo::k_hist_u8_cols<true><<<(unsigned)blocks, lo::kThreads, lo::kHistSmemBytes, s>>>(
-                (const uint8_t *)in->base, in->pitch, in->nrows, tiles_per_col, cnt, P, G);
-        else
-            lo::k_hist_u8_cols<false><<<(unsigned)blocks, lo::kThreads, lo::kHistSmemBytes, s>>>(
-                (const uint8_t *)in->base, in->pitch, in->nrows, tiles_per_col, cnt, P, G);
+        int mode = LO_U8_MODE_DEFAULT;
+        if (const char *e = getenv("LOEXEC_U8_MODE")) mode = atoi(e);       // measurement knob (scripts/u8_sweep.py)
+#define LO_U8_LAUNCH(AL, MD)                                                                             \
+    lo::k_hist_u8_cols<AL, MD><<<(unsigned)blocks, lo::kThreads, lo::kHistSmemBytes, s>>>(              \
+        (const uint8_t *)in->base, in->pitch, in->nrows, tiles_per_col, cnt, P, G)
+        if (!aligned)       LO_U8_LAUNCH(false, 4);
+        else if (mode == 2) LO_U8_LAUNCH(true, 2);
+        else if (mode == 5) LO_U8_LAUNCH(true, 5);
+        else if (mode == 6) LO_U8_LAUNCH(true, 6);
+        else                LO_U8_LAUNCH(true, 4);
+#undef LO_U8_LAUNCH
         LO_CUDA(cudaGetLastError());
         ctx->launches.fetch_add(1, std::memory_order_relaxed);
     }

@@ -35,10 +35,16 @@ enum : uint8_t {
     kInteger     = 1,   // finite and integer valued (is_integer())           -> the adapter stores int(v)
     kEmpty       = 2,   // exactly ""                                          -> None (data_type_update.py:37-38)
     kInvalid     = 3,   // float() would raise ValueError
-    kUnsupported = 4,   // non-ASCII byte or cell longer than kMaxLen: not decided on the device (job fails loudly)
+    kUnsupported = 4,   // byte >= 0x80 (the packer did not normalise the text, see below) or cell longer than kMaxLen
 };
 
-constexpr int kMaxLen    = 1024;   // bytes per cell handled on the device
+// CPython's float(str) first maps every non-ASCII character of the str: Unicode whitespace -> ' ', Unicode decimal
+// digits (category Nd, e.g. fullwidth or Arabic-Indic) -> '0'..'9', anything else -> invalid
+// (_PyUnicode_TransformDecimalAndSpaceToASCII).  That is a property lookup on code points, done by the host packer
+// (columnar.ascii_number_text) while it encodes the column; the device sees the normalised ASCII text and does all of
+// the arithmetic.  A raw byte >= 0x80 therefore means "not normalised" and is reported, never guessed.
+constexpr int kMaxLen    = 1 << 20;   // bytes per cell handled on the device (the algorithm itself has no length limit:
+                                      // digits beyond kMaxDigits only contribute a sticky bit)
 constexpr int kMaxDigits = 800;    // significant digits kept exactly in the slow path (a midpoint has <= 767)
 constexpr int kLimbs     = 168;    // 32-bit limbs of the slow path's big integers (5376 bits)
 

@@ -7,8 +7,9 @@ methods, in-place conversion of the input collection, same ``finished`` False ->
   The adapter keeps the reference's branch order around it: ``None`` untouched, ``""`` -> ``None``, the dead
   ``== int / == float`` checks, integer-valued results stored as ``int``; an unparsable cell raises
   ``ValueError`` after the earlier documents were updated, so the collection is left exactly as the
-  reference leaves it (``finished: False``).  Cells with non-ASCII bytes or > 1024 bytes are not decided on
-  the device and fail the job loudly (no host ``float()`` fallback).
+  reference leaves it (``finished: False``).  Unicode digits / whitespace (``"１２"``, ``"٣.٥"``) are mapped to ASCII by
+  the packer exactly as ``float(str)`` maps them (:func:`columnar.ascii_number_text`); a cell over 1 MiB fails the job
+  loudly (no host ``float()`` fallback).
 * ``"string"`` (``data_type_update.py:22-28``): ``str(v)`` / ``None -> ""`` is text formatting of Python
   objects in the document adapter and stays on the host (out of the GPU's scope).
 * ``"float32"`` (this build's optional extension): the B-semantics cast of SURVEY.md §0 — numeric values
@@ -84,8 +85,8 @@ class DataType:
                 if status[j] == N.LO_NUM_INVALID:
                     return updates, ValueError(f"could not convert string to float: {value!r}")
                 if status[j] == N.LO_NUM_UNSUPPORTED:
-                    return updates, RuntimeError(f"cell {value[:40]!r} (non-ASCII or > 1024 bytes) is not parsed on the "
-                                                 "device and there is no CPU fallback")
+                    return updates, RuntimeError(f"cell {value[:40]!r}... ({len(value)} characters) exceeds the device "
+                                                 "parser's 1 MiB cell limit and there is no CPU fallback")
                 new = float(parsed[j])
                 if status[j] == N.LO_NUM_INTEGER:
                     new = int(new)

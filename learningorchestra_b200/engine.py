@@ -315,9 +315,9 @@ class Engine:
     def parse_number_host(self, cells):
         """cells: list of ``str`` / ``bytes``.  Returns (values float64[n], status uint8[n]) — values are what
         CPython's ``float(cell)`` returns, status as LO_NUM_* (``_native``)."""
-        from .columnar import pack_cells
+        from .columnar import pack_number_cells
         n = len(cells)
-        chars, offsets = pack_cells(cells)
+        chars, offsets = pack_number_cells(cells)      # non-ASCII digits / whitespace normalised as float(str) does
         values = np.zeros(n, dtype=np.float64)
         status = np.zeros(n, dtype=np.uint8)
         N.check(self._lib.lo_parse_number_host(self._ctx, chars.ctypes.data_as(C.c_void_p), offsets.ctypes.data_as(C.c_void_p),

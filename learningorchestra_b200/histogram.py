@@ -56,7 +56,8 @@ class Histogram:
             if bins:
                 results = self.__binned(parent_filename, fields, int(bins), value_range)
             else:
-                documents = self.database_connector.find(parent_filename, {})  # unfiltered, like $group
+                # unfiltered, like $group; materialised once (a pymongo Cursor can be walked only once)
+                documents = list(self.database_connector.find(parent_filename, {}))
                 results = self.__value_counts(documents, fields)
             document_id = 1
             for field in fields:
@@ -97,15 +98,15 @@ class Histogram:
     def __binned(self, parent_filename, fields, bins, value_range):
         """Columns come from the GPU-resident copy of the dataset (built from the documents on first use,
         reused until the collection is written to): no document scan, no H2D on a repeat request."""
-        data = self.engine.resident.ensure(self.database_connector, parent_filename, fields)
-        cols = [data.column[f] for f in fields]            # nulls are NaN in the slabs: skipped by the kernel
-        if value_range is None:
-            lo, hi, _cnt = self.engine.minmax_cast(data.table, cols)
-        else:
-            lo = np.full(len(fields), value_range[0], np.float32)
-            hi = np.full(len(fields), value_range[1], np.float32)
-        dev_counts = self.engine.project_cast_hist(data.table, cols, bins, lo, hi)
-        counts = dev_counts.to_numpy()
-        dev_counts.free()
+        with self.engine.resident.lease(self.database_connector, parent_filename, fields) as data:
+            cols = [data.column[f] for f in fields]            # nulls are NaN in the slabs: skipped by the kernel
+            if value_range is None:
+                lo, hi = columnar.auto_range(*self.engine.minmax_cast(data.table, cols))   # constant / empty columns included
+            else:
+                lo = np.full(len(fields), value_range[0], np.float32)
+                hi = np.full(len(fields), value_range[1], np.float32)
+            dev_counts = self.engine.project_cast_hist(data.table, cols, bins, lo, hi)
+            counts = dev_counts.to_numpy()
+            dev_counts.free()
         return {f: {"bins": bins, "range": [float(lo[j]), float(hi[j])], "counts": [int(c) for c in counts[j]]}
                 for j, f in enumerate(fields)}

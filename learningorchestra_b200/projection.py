@@ -85,7 +85,7 @@ class Projection:
         counts = None
         if bins:
             if value_range is None:
-                lo, hi, _cnt = self.__engine.minmax_cast_host(cols)
+                lo, hi = columnar.auto_range(*self.__engine.minmax_cast_host(cols))
             else:
                 lo = np.full(len(selected), value_range[0], np.float32)
                 hi = np.full(len(selected), value_range[1], np.float32)

@@ -25,6 +25,8 @@ class ResidentDataset:
     def __init__(self, version, ids, fields, kinds, nulls, table):
         self.version, self.ids, self.fields, self.kinds, self.nulls, self.table = version, ids, fields, kinds, nulls, table
         self.column = {f: i for i, f in enumerate(fields)}
+        self.users = 0          # leases handed out and not yet released (guarded by ResidentTables._lock)
+        self.retired = False    # dropped from the cache: freed when the last user releases it
 
     @property
     def nbytes(self) -> int:
@@ -38,15 +40,43 @@ class ResidentTables:
         self._lock = threading.RLock()
         self.hits = self.misses = 0
 
+    def lease(self, database, filename: str, fields):
+        """``with resident.lease(db, name, fields) as data:`` — the table cannot be freed (version bump, eviction,
+        invalidate, another job's rebuild) while the block runs GPU work on it."""
+        cache = self
+
+        class _Lease:
+            def __enter__(self_inner):
+                self_inner.data = cache.ensure(database, filename, fields)
+                return self_inner.data
+
+            def __exit__(self_inner, *exc):
+                cache.release(self_inner.data)
+        return _Lease()
+
+    def release(self, entry: ResidentDataset) -> None:
+        with self._lock:
+            entry.users -= 1
+            if entry.retired and entry.users <= 0:
+                entry.table.free()
+
+    def _retire(self, entry: ResidentDataset) -> None:
+        """Called with the lock held: free now if nobody uses the table, else when the last lease ends."""
+        entry.retired = True
+        if entry.users <= 0:
+            entry.table.free()
+
     def ensure(self, database, filename: str, fields) -> ResidentDataset:
         """Resident table holding (at least) ``fields`` of ``filename``; built from the documents on a miss.
-        Raises ValueError if a requested field is not numeric."""
+        Raises ValueError if a requested field is not numeric.  The returned entry is LEASED: pair every call with
+        :meth:`release` (or use :meth:`lease`)."""
         version = database.version(filename) if hasattr(database, "version") else None
         with self._lock:
             entry = self._entries.get(filename)
             if entry is not None and version is not None and entry.version == version and all(f in entry.column for f in fields):
                 self._entries.move_to_end(filename)
                 self.hits += 1
+                entry.users += 1
                 return entry
             self.misses += 1
             keep = [f for f in (entry.fields if entry is not None and entry.version == version else []) if f not in fields]
@@ -63,12 +93,16 @@ class ResidentTables:
                 names.append(f); cols.append(packed[0]); kinds.append(packed[2]); nulls.append(int((~packed[1]).sum()))
             table = self.engine.table_from_numpy(cols) if rows else self.engine.table("f64", 0, max(len(cols), 1))
             new = ResidentDataset(version, np.array([d["_id"] for d in rows], dtype=np.int64), names, kinds, nulls, table)
+            new.users = 1
             if entry is not None:
-                entry.table.free()
+                self._entries.pop(filename, None)
+                self._retire(entry)
             if version is not None:
                 self._entries[filename] = new
                 self._entries.move_to_end(filename)
                 self._evict()
+            else:
+                new.retired = True         # never cached (foreign Database without version()): freed on release
             return new
 
     def _evict(self):
@@ -76,16 +110,16 @@ class ResidentTables:
         while total > self.max_bytes and len(self._entries) > 1:
             _name, old = self._entries.popitem(last=False)
             total -= old.nbytes
-            old.table.free()
+            self._retire(old)
 
     def invalidate(self, filename: str) -> None:
         with self._lock:
             entry = self._entries.pop(filename, None)
             if entry is not None:
-                entry.table.free()
+                self._retire(entry)
 
     def clear(self) -> None:
         with self._lock:
             for e in self._entries.values():
-                e.table.free()
+                self._retire(e)
             self._entries.clear()

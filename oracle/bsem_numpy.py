@@ -55,6 +55,30 @@ def bin_index_f32(x: np.ndarray, lo, hi, nbins: int) -> np.ndarray:
     return idx
 
 
+def auto_range(mins, maxs, nfinite):
+    """Range of a binned histogram request that carries no ``range``, per column, from the min /
+    max of the finite cast values.  B-semantics, frozen here (the reference defines no bins at all):
+
+    * no finite value (empty, all-null or all-NaN/inf column): [0, 1], as ``numpy.histogram`` does for empty input;
+    * constant column (min == max): [min - 0.5, max + 0.5] in fp32, again numpy's rule; where +-0.5 is below half an
+      ulp (|v| >= 2^24) the edges move to the neighbouring fp32 values instead, so hi > lo always holds;
+    * otherwise [min, max] unchanged."""
+    lo = np.array(mins, dtype=np.float32).copy()
+    hi = np.array(maxs, dtype=np.float32).copy()
+    n = np.asarray(nfinite)
+    for j in range(lo.shape[0]):
+        if n[j] == 0:
+            lo[j], hi[j] = np.float32(0.0), np.float32(1.0)
+        elif lo[j] == hi[j]:
+            a, b = np.float32(lo[j] - np.float32(0.5)), np.float32(hi[j] + np.float32(0.5))
+            if a == lo[j]:
+                a = np.nextafter(lo[j], np.float32(-np.inf), dtype=np.float32)
+            if b == hi[j]:
+                b = np.nextafter(hi[j], np.float32(np.inf), dtype=np.float32)
+            lo[j], hi[j] = a, b
+    return lo, hi
+
+
 def hist_f32(x: np.ndarray, lo, hi, nbins: int) -> np.ndarray:
     idx = bin_index_f32(x, lo, hi, nbins)
     return np.bincount(idx[idx >= 0], minlength=nbins).astype(np.uint64)

@@ -86,7 +86,12 @@ def main():
 
     # ---- per-value cast vectors through the reference's converter ---------------------
     vec_in = ["22", "0.42", "7.25", "1e3", "  5 ", "-0.0", "1_000", "nan", "inf", "-inf", "3.0", "9007199254740993",
-              "1e-400", "1.7976931348623159e308", "", None, "1e22", "0.1", "-7", "+8.50"]
+              "1e-400", "1.7976931348623159e308", "", None, "1e22", "0.1", "-7", "+8.50",
+              # what float(str) does with non-ASCII text: Unicode decimal digits and whitespace are mapped to ASCII first
+              "１２", "٣.٥", "\u2003 5\u00a0", "-１e２", "१२३.५०",
+              # cells far beyond the old 1024-byte device limit
+              "0." + "0" * 1500 + "25", "7" + "0" * 1100 + "e-1100", " " * 1200 + "42" + " " * 900,
+              "2.4703282292062327208051355972538996e-324" + "0" * 1500 + "1"]
     vdb = rsem.MemoryDatabase()
     vdb.insert_one_in_file("vec", {"_id": 0, "datasetName": "vec", "finished": True, "fields": ["v"]})
     for i, v in enumerate(vec_in, start=1):

@@ -82,11 +82,13 @@ def test_grammar_and_reference_cast_vectors(parse):
               "0.1", "0.2", "0.3", "0.30000000000000004", "123456789012345678", "1234567890123456789", "12345678901234567890",
               "123456789012345678901234567890", "0.000000000000000000000000000001", "1" + "0" * 400, "0." + "0" * 400 + "1",
               "1e99999999999999999999", "1e-99999999999999999999", "１２", "٣", "1 ", "é"]
+    from learningorchestra_b200.columnar import ascii_number_text
     bits, st = parse(cases)
     for s, b, t in zip(cases, bits, st):
-        if any(ord(ch) >= 0x80 for ch in s):
-            assert t == UNSUPPORTED, s          # documented: non-ASCII cells are not decided on the device
-            continue
+        assert t == UNSUPPORTED if any(ord(ch) >= 0x80 for ch in s) else t != UNSUPPORTED, s   # raw UTF-8 is reported, not guessed
+    # ... and through the packer's normalisation (what float(str) does first) every case is decided as CPython decides it
+    bits, st = parse([ascii_number_text(c) for c in cases])
+    for s, b, t in zip(cases, bits, st):
         es, eb = expected(s)
         assert t == es, (repr(s), int(t), es)
         if es in (FLOAT, INTEGER) and not math.isnan(struct.unpack("<d", struct.pack("<Q", eb))[0]):
@@ -150,10 +152,23 @@ def test_halfway_and_long_digit_strings(parse):
         digits = "".join(rng.choice("0123456789") for _ in range(d))
         pos = rng.randint(0, d)
         cases.append(digits[:pos] + "." + digits[pos:] + rng.choice(["", f"e{rng.randint(-340, 300)}"]))
-    check(parse, [c for c in cases if len(c) <= 1024])
+    check(parse, cases)
 
 
-def test_status_for_long_or_non_ascii(parse):
-    bits, st = parse(["1" * 1025, "0" * 1023 + "7", "é1", b"\xff", "1" * 1024])
-    assert st.tolist() == [UNSUPPORTED, INTEGER, UNSUPPORTED, UNSUPPORTED, FLOAT]
-    assert int(bits[1]) == struct.unpack("<Q", struct.pack("<d", 7.0))[0] and int(bits[4]) == 0x7FF0000000000000
+def test_long_cells_and_unicode_text(parse):
+    """No length limit short of 1 MiB: digits past the 800th only matter as a sticky bit.  Unicode decimal digits and
+    whitespace go through the packer's float(str) normalisation."""
+    from learningorchestra_b200.columnar import ascii_number_text
+    long_cases = ["1" * 1025, "0" * 5000 + "7", "1" * 400 + "." + "9" * 3000, "0." + "0" * 2000 + "123", "9" * 309, "9" * 308 + "." + "5" * 2000,
+                  "2.4703282292062327208051355972538996e-324" + "0" * 1500 + "1", " " * 1500 + "1e5" + "\t" * 900,
+                  "1" + "_0" * 700, "4.9e-324" + "0" * 2000, "1" + "0" * 1100 + "e-1100", "0" * 3000, "." + "0" * 3000 + "e5"]
+    check(parse, long_cases)
+    uni = ["１２", "٣.٥", "\u2003 5\u00a0", "１_０", "-１e２", "é1", "1é", "１٣.５e-１", "\u30001\u3000", "१२३", "1\u00b2", "½", "\x1c5", "5\x85"]
+    bits, st = parse([ascii_number_text(c) for c in uni])
+    for s, b, t in zip(uni, bits, st):
+        es, eb = expected(s)
+        assert t == es, (repr(s), int(t), es)
+        if es in (FLOAT, INTEGER):
+            assert int(b) == eb, (s, hex(int(b)), hex(eb))
+    bits, st = parse(["é1", b"\xff", "1" * ((1 << 20) + 1)])
+    assert st.tolist() == [UNSUPPORTED, UNSUPPORTED, UNSUPPORTED]
