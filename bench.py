@@ -352,18 +352,24 @@ def run_gpu(args) -> int:
     nrows = table.local_rows
     torch.cuda.synchronize()
 
-    kev = []   # (start, end) events around the library call of one step, for the roofline
+    kev = []   # (start, end) events around the library call of one ISOLATED step (no overlap with its neighbours)
+    # Timed steps are independent jobs over the same resident table (each step re-reads its inputs and rewrites its
+    # outputs; nothing is carried from step to step), so they are issued with LO_GROUP_INDEPENDENT: the next step's
+    # CTAs may fill the SMs that the previous step's last wave leaves idle (programmatic dependent launch).  Every
+    # step still does all of its work; --no-overlap serialises them completely, as round 1 did.
+    overlap = not args.no_overlap
 
     def step(record: bool):
         if record:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
+        ind = overlap and not record          # an event record between two launches serialises them anyway
         if w == "s100":
-            sh.project_cast_hist(table, cols, NBINS, lo, hi, out=out, streams=streams)
+            sh.project_cast_hist(table, cols, NBINS, lo, hi, out=out, streams=streams, independent=ind)
         elif w == "s10":
             sh.project_cast(table, cols, out=out, streams=streams)
         else:
-            sh.hist_u8_cols(table, cols, streams=streams)
+            sh.hist_u8_cols(table, cols, streams=streams, independent=ind)
         if record:
             e1.record(stream)
             kev.append((e0, e1))
@@ -388,11 +394,14 @@ def run_gpu(args) -> int:
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_start.record(stream)
     for _ in range(args.steps):
-        step(True)
+        step(False)
     t_end.record(stream)
     torch.cuda.synchronize()
     sampler.mark_end()
     launches = eng.launch_count - launches0 - 1          # the barrier launch is outside the timed region
+    for _ in range(5):                                   # the same step in isolation (event-bracketed, serialised)
+        step(True)
+    torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -402,7 +411,9 @@ def run_gpu(args) -> int:
     t = torch.tensor([elapsed_ms, sum(kernel_ms) / len(kernel_ms)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms, kernel_ms_avg = float(t[0]), float(t[1])
+    elapsed_ms, kernel_ms_isolated = float(t[0]), float(t[1])
+    # average duration of the kernel over the timed region: one launch per step, back to back on one stream
+    kernel_ms_avg = elapsed_ms / args.steps
     assert sh.timeouts() == 0, "a device-side wait of the merge timed out"
 
     # ---- parity of THIS run against the oracle-made goldens (every N, every workload) ---------------------
@@ -519,7 +530,7 @@ def run_gpu(args) -> int:
             "data": "synthetic",
             "config": {"workload": workload_text(w, total_rows, ncols, k), "name": w,
                        "rows": total_rows, "cols": ncols, "k": k, "nbins": NBINS if w != "s10" else 0, "rows_per_gpu": nrows,
-                       "merge": sh.merge if world > 1 else None,
+                       "merge": sh.merge if world > 1 else None, "steps_overlap": bool(overlap and w != "s10"),
                        "parallelism": (f"row-range shards x{world}, " + (
                            f"one NCCL all-reduce of {k}x{NBINS} uint64 per step (inside libloexec)" if sh.merge == "nccl" else
                            "merge inside the streaming kernel: column-last CTAs push with system-scope RED.64 into rank 0's "
@@ -532,7 +543,10 @@ def run_gpu(args) -> int:
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src, "kernel": W["kernel"],
                          "kernel_ms_avg": kernel_ms_avg, "algorithmic_bytes_per_launch": alg_bytes,
-                         "overhead_us_per_step": (elapsed_ms / args.steps - kernel_ms_avg) * 1e3},
+                         "kernel_ms_isolated": kernel_ms_isolated,
+                         "note": ("kernel_ms_avg = timed region / steps (one launch per step, merge included"
+                                  + (", consecutive launches allowed to overlap their predecessor's draining last wave" if overlap and w != "s10" else "")
+                                  + "); kernel_ms_isolated = the same launch alone between two CUDA events, 5 samples after the timed region")},
             "parity": parity, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         }
         if cpu:
@@ -577,6 +591,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true",
+                    help="serialise consecutive steps completely (no programmatic dependent launch between them)")
     ap.add_argument("--merge", default="auto", choices=["auto", "nccl", "p2p", "peer"],
                     help="N > 1: how partial histograms are merged (in-kernel peer-memory merge, or NCCL all-reduce)")
     args = ap.parse_args()

@@ -207,6 +207,10 @@ typedef struct lo_group lo_group;
 #define LO_MERGE_PEER 1
 #define LO_MERGE_NCCL 2
 #define LO_GROUP_BCAST 1  /* call flag: every member receives the merged matrix (all-reduce); default: root only */
+#define LO_GROUP_INDEPENDENT 2 /* call flag (lo_group_*_dev): this step reads nothing the PREVIOUS group step on the same
+                                * streams wrote, so its CTAs may start while that step's last wave is still draining
+                                * (programmatic dependent launch; the steps use alternating accumulate matrices).  Other
+                                * work on the stream — and a step without the flag — still waits for full completion. */
 
 int lo_group_create_local(lo_ctx *const *ctxs, int32_t n, int32_t merge, lo_group **out);
 int lo_group_rank_begin(lo_ctx *ctx, int32_t rank, int32_t world, int32_t merge, lo_group **out,

@@ -28,6 +28,7 @@ LO_SYNTH_UNIFORM, LO_SYNTH_EDGES, LO_SYNTH_CONSTCOL, LO_SYNTH_MNIST_U8 = 0, 1, 2
 LO_MAX_BINS = 256
 LO_MERGE_AUTO, LO_MERGE_PEER, LO_MERGE_NCCL = 0, 1, 2
 LO_GROUP_BCAST = 1
+LO_GROUP_INDEPENDENT = 2
 LO_GROUP_BLOB_BYTES = 512
 LO_GROUP_MAX_DEVICES = 16
 LO_GROUP_MAX_COUNTS = 262144

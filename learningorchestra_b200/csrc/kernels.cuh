@@ -103,6 +103,10 @@ constexpr int kMaxPeers = 15;
 struct GroupStep {
     int mode;                          // 0: no group (plain accumulate into counts);  1: merge as described
     int is_root, npeers, epilogue_in_kernel;
+    int overlap, pad_;                 // 1: launched with programmatic stream serialization: let the NEXT launch's CTAs
+                                       //    take the SMs this one's tail leaves idle (LO_GROUP_INDEPENDENT)
+    unsigned long long *gen;           // steps of this parity whose pushes have completed on this device
+    unsigned long long gen_target;     // flush only once *gen >= gen_target (the step two launches back is done)
     unsigned long long *local;         // this device's accumulate matrix (zero at entry, left zero at exit)
     unsigned long long *shared;        // root's merge matrix of this step's parity (peer-mapped on the others)
     unsigned long long *arrived;       // root's arrival counter of this parity
@@ -332,6 +336,25 @@ __device__ __forceinline__ void group_root_epilogue(const GroupStep &G, int n, i
     }
 }
 
+// Overlapped launches (GroupStep.overlap): before a CTA touches this parity's accumulate matrix or tickets, the step
+// two launches back (same parity) must have finished pushing.  By the time a CTA has streamed its tile this is
+// virtually always true already; the wait only matters for formal safety.  All of that step's CTAs are resident (the
+// launch in between could not have started otherwise), so waiting here cannot starve them.
+__device__ __forceinline__ void group_wait_generation(const GroupStep &G) {
+    if (G.gen_target == 0ull) return;
+    if (threadIdx.x == 0) {
+        unsigned long long v;
+        const unsigned long long t0 = globaltimer_ns();
+        for (;;) {
+            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(G.gen) : "memory");
+            if (v >= G.gen_target) break;
+            if (globaltimer_ns() - t0 > G.timeout_ns) { atomicAdd(G.timed_out, 1ull); break; }
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+}
+
 // Called by every thread of a CTA after its tile's REDs into G.local were issued.  j: projected column, nb: its bins,
 // k: columns of this launch.  Uses one word of shared memory (`sflag`, any smem word the caller no longer needs).
 __device__ __forceinline__ void group_finish_column(const GroupStep &G, unsigned j, int nb, int k, unsigned tiles_per_col,
@@ -366,6 +389,8 @@ __device__ __forceinline__ void group_finish_column(const GroupStep &G, unsigned
             *G.done_ticket = 0u;
             __threadfence_system();
             red_release_sys_add(G.arrived, 1ull);
+            // this parity's accumulate matrix and tickets are clean again: the launch after next may flush into them
+            asm volatile("red.release.gpu.global.add.u64 [%0], %1;" :: "l"(G.gen), "l"(1ull) : "memory");
         }
         *sflag = (last && G.is_root && G.epilogue_in_kernel) ? 2u : 0u;
         if (*sflag == 2u && !wait_flag_ge(G.arrived, G.arrive_target, G.timeout_ns, G.timed_out)) *sflag = 3u;
@@ -390,6 +415,8 @@ k_project_cast_hist(const char *__restrict__ in_base, long long in_pitch,
                     const __grid_constant__ ColsF64 P, const __grid_constant__ TileMap M,
                     const __grid_constant__ GroupStep G) {
     extern __shared__ uint32_t smem[];
+    // overlapped steps: the next launch may start filling SMs as soon as every CTA of this one is resident
+    if (G.overlap) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     // blockIdx -> (column j, rows [r0, r0 + n)): full-size tiles first, the short tiles of the tapered tail last
     unsigned j, tile;
     int nbatches;
@@ -523,6 +550,7 @@ k_project_cast_hist(const char *__restrict__ in_base, long long in_pitch,
             fold_and_flush(smem, rows, P.nbins, counts + (long long)j * P.nbins);
         } else {
             // multi-GPU merge riding on the flush: accumulate on this device, the column's last tile pushes to the root
+            group_wait_generation(G);
             fold_and_flush(smem, rows, P.nbins, G.local + (long long)j * P.nbins);
             group_finish_column(G, j, P.nbins, P.k, M.tiles_a + M.tiles_b, smem);
         }
@@ -808,6 +836,7 @@ k_hist_u8_cols(const uint8_t *__restrict__ in_base, long long in_pitch, long lon
                unsigned tiles_per_col, unsigned long long *__restrict__ counts,
                const __grid_constant__ ColsU8 P, const __grid_constant__ GroupStep G) {
     extern __shared__ uint32_t smem[];
+    if (G.overlap) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const unsigned j    = blockIdx.x / tiles_per_col;
     const unsigned tile = blockIdx.x - j * tiles_per_col;
     const long long r0  = (long long)tile * kU8TileRows;
@@ -849,6 +878,7 @@ k_hist_u8_cols(const uint8_t *__restrict__ in_base, long long in_pitch, long lon
     if (G.mode == 0) {
         fold_and_flush(smem, kHistRows, 256, counts + (long long)j * 256);
     } else {
+        group_wait_generation(G);
         fold_and_flush(smem, kHistRows, 256, G.local + (long long)j * 256);
         group_finish_column(G, j, 256, P.k, tiles_per_col, smem);
     }
@@ -967,6 +997,7 @@ k_group_push(const __grid_constant__ GroupStep G, int n, int op) {
     if (threadIdx.x == 0) {
         __threadfence_system();
         red_release_sys_add(G.arrived, 1ull);
+        asm volatile("red.release.gpu.global.add.u64 [%0], %1;" :: "l"(G.gen), "l"(1ull) : "memory");
         state = G.is_root ? (wait_flag_ge(G.arrived, G.arrive_target, G.timeout_ns, G.timed_out) ? 2 : 3) : 0;
     }
     __syncthreads();

@@ -17,6 +17,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace {
@@ -217,6 +218,25 @@ lo::TileMap make_tilemap(const lo_ctx *ctx, int64_t nrows, int32_t k) {
 
 const lo::GroupStep kNoGroup = {};     // mode 0
 
+// <<<>>> with one optional launch attribute: programmatic stream serialization lets THIS launch's CTAs start as soon
+// as every CTA of the previous launch in the stream has called griddepcontrol.launch_dependents (or exited) instead
+// of after its last CTA has drained (overlapped group steps, LO_GROUP_INDEPENDENT)
+template <typename... KArgs, typename... Args>
+cudaError_t launch_kernel(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t s, bool overlap,
+                          Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = overlap ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 // one launch of the fused kernel over <= kMaxColsF64 projected columns
 template <int OUT, bool HIST>
 int launch_f64(lo_ctx *ctx, const lo_table *in, const lo_table *out, int32_t out_col0,
@@ -253,9 +273,11 @@ int launch_f64(lo_ctx *ctx, const lo_table *in, const lo_table *out, int32_t out
     const lo::TileMap M = make_tilemap(ctx, in->nrows, P.k);
     const unsigned long long blocks = ((unsigned long long)M.tiles_a + M.tiles_b) * (unsigned)P.k;
     if (blocks > 0x7fffffffull) return fail(LO_ERR_INVALID, "table too large for one launch (%llu tiles)", blocks);
-#define LO_LAUNCH(AL, FD)                                                                              \
-    lo::k_project_cast_hist<OUT, HIST, AL, FD><<<(unsigned)blocks, lo::kThreads, smem, s>>>(           \
-        in->base, in->pitch, out_base, out_pitch, in->nrows, counts, P, M, G)
+    const char *ib = in->base;
+    const long long ip = in->pitch, nr = in->nrows;
+#define LO_LAUNCH(AL, FD)                                                                                        \
+    LO_CUDA(launch_kernel(lo::k_project_cast_hist<OUT, HIST, AL, FD>, (unsigned)blocks, lo::kThreads, smem, s,    \
+                          G.overlap != 0, ib, ip, out_base, out_pitch, nr, counts, P, M, G))
     if (aligned) { if (fast) LO_LAUNCH(true, true); else LO_LAUNCH(true, false); }
     else         { if (fast) LO_LAUNCH(false, true); else LO_LAUNCH(false, false); }
 #undef LO_LAUNCH
@@ -339,9 +361,11 @@ int hist_u8_impl(lo_ctx *ctx, const lo_table *in, const int32_t *col_idx, int32_
         unsigned long long *cnt = (unsigned long long *)counts_dev + (int64_t)c0 * 256;
         int mode = LO_U8_MODE_DEFAULT;
         if (const char *e = getenv("LOEXEC_U8_MODE")) mode = atoi(e);       // measurement knob (scripts/u8_sweep.py)
-#define LO_U8_LAUNCH(AL, MD)                                                                             \
-    lo::k_hist_u8_cols<AL, MD><<<(unsigned)blocks, lo::kThreads, lo::kHistSmemBytes, s>>>(              \
-        (const uint8_t *)in->base, in->pitch, in->nrows, tiles_per_col, cnt, P, G)
+        const uint8_t *ib = (const uint8_t *)in->base;
+        const long long ip = in->pitch, nr = in->nrows;
+#define LO_U8_LAUNCH(AL, MD)                                                                                      \
+    LO_CUDA(launch_kernel(lo::k_hist_u8_cols<AL, MD>, (unsigned)blocks, lo::kThreads, (size_t)lo::kHistSmemBytes, s, \
+                          G.overlap != 0, ib, ip, nr, tiles_per_col, cnt, P, G))
         if (!aligned)       LO_U8_LAUNCH(false, 4);
         else if (mode == 2) LO_U8_LAUNCH(true, 2);
         else if (mode == 5) LO_U8_LAUNCH(true, 5);

@@ -40,6 +40,8 @@ class DataType:
         self.last_job = None
 
     def field_converter(self, filename, field, field_type):
+        if getattr(self.database_connector, "has_columns", lambda _f: False)(filename):
+            return self.__convert_column(filename, field, field_type)
         rows = columnar.data_rows(self.database_connector.find(filename, {}))
         failure = None
         if field_type == self.FLOAT32_TYPE:
@@ -53,6 +55,67 @@ class DataType:
         self.database_connector.update_by_id(filename, changes)
         if failure is not None:
             raise failure
+
+    def __convert_column(self, filename, field, field_type):
+        """The same conversions on a collection stored as columns (:mod:`column_store`): the text column's Arrow
+        buffers are the parser's input, the result is a new NumberColumn — no per-document round trip at all (the
+        reference does one ``update_one`` per document per field, ``data_type_update.py:45``)."""
+        from . import _native as N
+        from .column_store import NumberColumn, ObjectColumn, TextColumn
+        db = self.database_connector
+        col = db.column(filename, field)
+        if col is None:
+            raise KeyError(field)                       # reference: document[field] raises KeyError on the first row
+        if col.kind == "object":                       # mixed cells: the per-document definition decides
+            db.to_documents(filename)
+            return self.field_converter(filename, field, field_type)
+        if field_type == self.STRING_TYPE:
+            if col.kind == "text":                     # str(v) of a str is itself; None -> ""
+                new = TextColumn(col.arr.fill_null("")) if col.arr.null_count else col
+            else:                                      # str(int) / repr(float): text formatting stays on the host (a5)
+                import pyarrow as pa
+                new = TextColumn(pa.array(["" if v is None else str(v) for v in col.to_pylist()], type=pa.large_string()))
+            db.set_column(filename, field, new)
+        elif field_type == self.NUMBER_TYPE:
+            if self.engine is None:
+                raise RuntimeError("type 'number' parses text on the GPU and needs an Engine (there is no CPU fallback)")
+            if col.kind == "number":                   # float(v); is_integer() -> int(v)
+                v = col.values
+                integral = col.valid & np.isfinite(v) & (v == np.floor(v))
+                db.set_column(filename, field, NumberColumn(v, col.valid, integral))
+                return
+            import pyarrow.compute as pc
+            arr = col.arr
+            if not pc.all(pc.string_is_ascii(arr.fill_null(""))).as_py():      # Unicode digits / spaces, as float(str)
+                import pyarrow as pa
+                arr = pa.array([None if c is None else columnar.ascii_number_text(c) for c in arr.to_pylist()], type=pa.large_string())
+            chars, offsets, nulls = TextColumn(arr).packed()
+            values, status = self.engine.parse_number_packed(chars, offsets)
+            bad = np.flatnonzero((status == N.LO_NUM_INVALID) | (status == N.LO_NUM_UNSUPPORTED))
+            if nulls is not None:
+                bad = bad[~nulls[bad]]
+            if bad.size:
+                # the reference converts document by document and dies on the first bad cell: earlier rows converted,
+                # the rest untouched, finished stays False
+                first = int(bad[0])
+                cells = col.to_pylist()
+                head = NumberColumn(values[:first], (status[:first] <= N.LO_NUM_INTEGER), status[:first] == N.LO_NUM_INTEGER).to_pylist()
+                db.set_column(filename, field, ObjectColumn(head + cells[first:]))
+                if status[first] == N.LO_NUM_UNSUPPORTED:
+                    raise RuntimeError(f"cell of {len(cells[first])} characters exceeds the device parser's 1 MiB limit "
+                                       "and there is no CPU fallback")
+                raise ValueError(f"could not convert string to float: {cells[first]!r}")
+            valid = status <= N.LO_NUM_INTEGER           # "" (and None) -> None
+            db.set_column(filename, field, NumberColumn(np.where(valid, values, np.nan), valid, status == N.LO_NUM_INTEGER))
+        elif field_type == self.FLOAT32_TYPE:
+            if col.kind != "number":
+                raise ValueError(f"field {field!r} is not numeric; convert it to 'number' first")
+            if self.engine is None:
+                raise RuntimeError("type 'float32' needs an Engine (there is no CPU fallback)")
+            out = np.empty(len(col), dtype=np.float32)
+            self.engine.project_cast_hist_host([np.ascontiguousarray(col.values)], None, out=[out])
+            db.set_column(filename, field, NumberColumn(np.where(col.valid, out.astype(np.float64), np.nan), col.valid))
+        # unknown type: the reference issues an empty $set
 
     def __to_text(self, rows, field):
         """``data_type_update.py:22-28``: ``None -> ""``, anything else ``str(v)``; the reference's guard

@@ -324,6 +324,36 @@ class Engine:
                                                n, values.ctypes.data_as(C.c_void_p), status.ctypes.data_as(C.c_void_p), None))
         return values, status
 
+    def parse_number_packed(self, chars: np.ndarray, offsets: np.ndarray):
+        """The same on an already packed column (chars uint8, offsets int64[n+1]) — e.g. the buffers of an Arrow
+        ``large_string`` array, untouched.  The text must be ASCII-normalised (:func:`columnar.ascii_number_text`)."""
+        n = offsets.shape[0] - 1
+        values = np.zeros(n, dtype=np.float64)
+        status = np.zeros(n, dtype=np.uint8)
+        if n:
+            N.check(self._lib.lo_parse_number_host(self._ctx, chars.ctypes.data_as(C.c_void_p), offsets.ctypes.data_as(C.c_void_p),
+                                                   n, values.ctypes.data_as(C.c_void_p), status.ctypes.data_as(C.c_void_p), None))
+        return values, status
+
+    def value_counts_str_packed(self, chars: np.ndarray, offsets: np.ndarray):
+        """(rep_rows int64[g], counts uint64[g]) of an already packed text column (offsets[0] == 0)."""
+        n = offsets.shape[0] - 1
+        if n == 0:
+            return np.zeros(0, np.int64), np.zeros(0, np.uint64)
+        cap = max(min(n, 1 << 16), 1)
+        while True:
+            rows = np.empty(cap, dtype=np.int64)
+            counts = np.empty(cap, dtype=np.uint64)
+            nd = C.c_int64()
+            rc = self._lib.lo_value_counts_str_host(self._ctx, chars.ctypes.data_as(C.c_void_p), offsets.ctypes.data_as(C.c_void_p),
+                                                    n, rows.ctypes.data_as(C.c_void_p), counts.ctypes.data_as(C.c_void_p),
+                                                    cap, C.byref(nd), None)
+            if rc == N.LO_ERR_INVALID and nd.value > cap:
+                cap = int(nd.value)
+                continue
+            N.check(rc)
+            return rows[:nd.value], counts[:nd.value]
+
     def value_counts_f64_host(self, values: np.ndarray):
         """(keys float64[g], counts uint64[g]) — exact value counts of a numeric column (GPU hash group-by),
         -0.0 grouped with 0.0 and all NaNs together; order unspecified."""

@@ -21,6 +21,7 @@ columns that arrive already encoded (e.g. the uint8 tables of config M).
 """
 from __future__ import annotations
 
+import math
 from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
@@ -55,6 +56,8 @@ class Histogram:
                 raise RuntimeError("Histogram needs an Engine: the counting has no CPU fallback")
             if bins:
                 results = self.__binned(parent_filename, fields, int(bins), value_range)
+            elif getattr(self.database_connector, "has_columns", lambda _f: False)(parent_filename):
+                results = self.__value_counts_columnar(parent_filename, fields)
             else:
                 # unfiltered, like $group; materialised once (a pymongo Cursor can be walked only once)
                 documents = list(self.database_connector.find(parent_filename, {}))
@@ -91,6 +94,53 @@ class Histogram:
                 groups = [{"_id": values[present[int(r)]], "count": int(c)} for r, c in zip(rep, counts)]
             if len(present) != len(values):                              # None / missing (metadata document included)
                 groups.append({"_id": None, "count": len(values) - len(present)})
+            results[f] = groups
+        return results
+
+    def __value_counts_columnar(self, parent_filename, fields):
+        """The same ``$group`` on a collection whose rows are stored as columns (:mod:`column_store`): a text field's
+        Arrow buffers (chars + offsets) go to the byte-wise GPU group-by untouched, a number field's float64 array to
+        the binary64 group-by — no document is materialised.  Documents that are not data rows (the metadata document)
+        have none of the fields and count under ``null``, as in the reference."""
+        db = self.database_connector
+        others = db.other_documents(parent_filename)
+        nrows = db.nrows(parent_filename)
+        results = {}
+        for f in fields:
+            col = db.column(parent_filename, f)
+            none_count = sum(1 for d in others if d.get(f) is None)
+            extra = [d[f] for d in others if d.get(f) is not None]
+            if col is None:
+                groups, none_count = [], none_count + nrows
+            elif col.kind == "number":
+                keys, counts = self.engine.value_counts_f64_host(col.values[col.valid]) if col.valid.any() else ([], [])
+                as_int = col.integers_collapsed
+                groups = [{"_id": (int(k) if as_int and math.isfinite(k) and float(k).is_integer() else float(k)), "count": int(c)}
+                          for k, c in zip(keys, counts)]
+                none_count += int((~col.valid).sum())
+            elif col.kind == "text":
+                arr = col.arr.drop_null() if col.arr.null_count else col.arr
+                none_count += col.arr.null_count
+                from .column_store import TextColumn
+                chars, offsets, _ = TextColumn(arr).packed()
+                rep, counts = self.engine.value_counts_str_packed(chars, offsets)
+                keys = arr.take(__import__("pyarrow").array(rep, type=__import__("pyarrow").int64())).to_pylist() if len(rep) else []
+                groups = [{"_id": k, "count": int(c)} for k, c in zip(keys, counts)]
+            else:                                    # mixed-type column: the document path's tagged byte-wise group-by
+                sub = self.__value_counts([{f: v} for v in col.to_pylist()], [f])[f]
+                none_count += sum(g["count"] for g in sub if g["_id"] is None)
+                groups = [g for g in sub if g["_id"] is not None]
+            if extra:                                # (result documents with the field: not produced by this stack)
+                merged = self.__value_counts([{f: v} for v in extra], [f])[f]
+                index = {columnar.group_key(g["_id"]): g for g in groups}
+                for g in merged:
+                    hit = index.get(columnar.group_key(g["_id"]))
+                    if hit:
+                        hit["count"] += g["count"]
+                    else:
+                        groups.append(g)
+            if none_count:
+                groups.append({"_id": None, "count": none_count})
             results[f] = groups
         return results
 

@@ -50,6 +50,12 @@ class Projection:
         try:
             source = Database.collection_from_url(database_url_input)
             target = Database.collection_from_url(database_url_output)
+            if getattr(database, "has_columns", lambda _f: False)(source):
+                fields_with_id = self.__project_columns(database, source, target, list(fields), cast_to, bins, value_range)
+                fields.append(self.__DOCUMENT_ID)        # projection.py:42 mutates the caller's list; kept
+                del fields_with_id
+                self.__metadata_creator.update_finished_flag(projection_filename, True)
+                return
             rows = columnar.data_rows(database.find(source, {}))
             selected = list(fields)
             fields.append(self.__DOCUMENT_ID)       # projection.py:42 mutates the caller's list; kept
@@ -69,6 +75,52 @@ class Projection:
         except BaseException as exc:                # reference: exception lost, finished stays False
             record_exception(database, projection_filename, exc)
             raise
+
+    def __project_columns(self, database, source, target, selected, cast_to, bins, value_range):
+        """``select(*fields, "_id")`` on a collection stored as columns (:mod:`column_store`): the output collection
+        shares the selected column arrays (they are immutable) — no row is touched.  With ``cast_to="float32"`` the
+        columns come from / go through the HBM-resident copy of the dataset and the fused kernel."""
+        from .column_store import NumberColumn
+        ids = database.row_ids(source)
+        if cast_to is None:
+            cols = {}
+            for f in selected:
+                c = database.column(source, f)
+                cols[f] = c if c is not None else NumberColumn(np.full(ids.shape[0], np.nan), np.zeros(ids.shape[0], bool))
+            database.create_table(target, ids, cols)
+            return selected
+        if cast_to != "float32":
+            raise ValueError(f"unknown cast_to {cast_to!r}")
+        if self.__engine is None:
+            raise RuntimeError("cast_to needs an Engine in the spark_session slot (there is no CPU fallback)")
+        with self.__engine.resident.lease(database, source, selected) as data:
+            idx = [data.column[f] for f in selected]
+            out = None
+            try:
+                if bins:
+                    if value_range is None:
+                        lo, hi = columnar.auto_range(*self.__engine.minmax_cast(data.table, idx))
+                    else:
+                        lo = np.full(len(selected), value_range[0], np.float32)
+                        hi = np.full(len(selected), value_range[1], np.float32)
+                    out = self.__engine.table("f32", data.table.nrows, len(selected))
+                    dev = self.__engine.project_cast_hist(data.table, idx, int(bins), lo, hi, out=out)
+                    counts = dev.to_numpy()
+                    dev.free()
+                    database.update_one(target, {"histogram": {
+                        f: {"bins": int(bins), "range": [float(lo[j]), float(hi[j])], "counts": [int(c) for c in counts[j]]}
+                        for j, f in enumerate(selected)}}, {"_id": 0})
+                else:
+                    out = self.__engine.project_cast(data.table, idx)
+                cols = {}
+                for j, f in enumerate(selected):
+                    src = database.column(source, f)
+                    cols[f] = NumberColumn(np.where(src.valid, out.to_numpy(j).astype(np.float64), np.nan), src.valid)
+            finally:
+                if out is not None:
+                    out.free()
+        database.create_table(target, database.row_ids(source), cols)
+        return selected
 
     def __gpu_cast(self, database, target, rows, ids, selected, bins, value_range):
         if self.__engine is None:

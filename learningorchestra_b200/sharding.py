@@ -275,16 +275,21 @@ class ShardedEngine:
             return None
         return (C.c_void_p * self.nlocal)(*[_stream_ptr(s) for s in streams])
 
+    def _flags(self, bcast: bool, independent: bool) -> int:
+        return (self._N.LO_GROUP_BCAST if bcast else 0) | (self._N.LO_GROUP_INDEPENDENT if independent else 0)
+
     def project_cast_hist(self, table: ShardedTable, col_idx, nbins: int, lo, hi, out: ShardedTable | None = None,
-                          bcast: bool = False, streams=None) -> GroupCounts:
+                          bcast: bool = False, streams=None, independent: bool = False) -> GroupCounts:
         """One step over all shards: fused projection + cast + histogram on every member, partial histograms merged
-        inside the kernels.  Asynchronous; the merged counts are read with ``.to_numpy()`` / :meth:`result`."""
+        inside the kernels.  Asynchronous; the merged counts are read with ``.to_numpy()`` / :meth:`result`.
+        ``independent``: this step reads nothing the previous group step wrote (another job, or the same inputs
+        again), so it may start while that step's last wave is still draining."""
         from .engine import _i32
         idx, k = _i32(col_idx)
         spec, _keep = self.engines[0]._spec(k, nbins, lo, hi)
         self._N.check(self._lib.lo_group_project_cast_hist_dev(
             self._g, self._tables(table), idx, k, self._tables(out), C.byref(spec),
-            self._N.LO_GROUP_BCAST if bcast else 0, self._streams(streams)))
+            self._flags(bcast, independent), self._streams(streams)))
         return GroupCounts(self, k, nbins)
 
     def project_cast(self, table: ShardedTable, col_idx, out: ShardedTable | None = None, out_dtype: str = "f32",
@@ -296,11 +301,11 @@ class ShardedEngine:
             e.project_cast(table.shards[i], col_idx, out=out.shards[i], stream=streams[i] if streams else None)
         return out
 
-    def hist_u8_cols(self, table: ShardedTable, col_idx, bcast: bool = False, streams=None) -> GroupCounts:
+    def hist_u8_cols(self, table: ShardedTable, col_idx, bcast: bool = False, streams=None, independent: bool = False) -> GroupCounts:
         from .engine import _i32
         idx, k = _i32(col_idx)
         self._N.check(self._lib.lo_group_hist_u8_cols_dev(self._g, self._tables(table), idx, k,
-                                                          self._N.LO_GROUP_BCAST if bcast else 0, self._streams(streams)))
+                                                          self._flags(bcast, independent), self._streams(streams)))
         return GroupCounts(self, k, 256)
 
     def minmax_cast(self, table: ShardedTable, col_idx, streams=None):
@@ -390,6 +395,12 @@ class ShardedEngine:
 
     def parse_number_host(self, cells):
         return self.engines[0].parse_number_host(cells)
+
+    def parse_number_packed(self, chars, offsets):
+        return self.engines[0].parse_number_packed(chars, offsets)
+
+    def value_counts_str_packed(self, chars, offsets):
+        return self.engines[0].value_counts_str_packed(chars, offsets)
 
     def value_counts_f64_host(self, values):
         return self.engines[0].value_counts_f64_host(values)

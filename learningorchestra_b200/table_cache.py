@@ -81,18 +81,33 @@ class ResidentTables:
             self.misses += 1
             keep = [f for f in (entry.fields if entry is not None and entry.version == version else []) if f not in fields]
             wanted = list(fields) + keep
-            rows = columnar.data_rows(database.find(filename, {}))
-            rows.sort(key=lambda d: d["_id"])
+            columnar_rows = getattr(database, "has_columns", lambda _f: False)(filename)
+            if columnar_rows:            # rows already stored as columns (column_store): no document is touched
+                row_ids = database.row_ids(filename)
+                rows = row_ids
+            else:
+                rows = columnar.data_rows(database.find(filename, {}))
+                rows.sort(key=lambda d: d["_id"])
+                row_ids = np.array([d["_id"] for d in rows], dtype=np.int64)
             cols, kinds, nulls, names = [], [], [], []
             for f in wanted:
-                packed = columnar.numeric_column([d.get(f) for d in rows])
+                if columnar_rows:
+                    c = database.column(filename, f)
+                    if c is not None and c.kind == "object":
+                        packed = columnar.numeric_column(c.to_pylist())
+                    elif c is not None and c.kind == "number":
+                        packed = (np.where(c.valid, c.values, np.nan), c.valid, "int" if c.is_int[c.valid].all() else "float")
+                    else:
+                        packed = None
+                else:
+                    packed = columnar.numeric_column([d.get(f) for d in rows])
                 if packed is None:
                     if f in fields:
                         raise ValueError(f"field {f!r} is not numeric; run /fieldTypes first")
                     continue                 # a previously resident column that stopped being numeric: drop it
                 names.append(f); cols.append(packed[0]); kinds.append(packed[2]); nulls.append(int((~packed[1]).sum()))
-            table = self.engine.table_from_numpy(cols) if rows else self.engine.table("f64", 0, max(len(cols), 1))
-            new = ResidentDataset(version, np.array([d["_id"] for d in rows], dtype=np.int64), names, kinds, nulls, table)
+            table = self.engine.table_from_numpy(cols) if len(rows) and cols else self.engine.table("f64", 0, max(len(cols), 1))
+            new = ResidentDataset(version, row_ids, names, kinds, nulls, table)
             new.users = 1
             if entry is not None:
                 self._entries.pop(filename, None)

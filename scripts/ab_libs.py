@@ -21,8 +21,8 @@ for _ in range(15):
 torch.cuda.synchronize(); ts = sorted(x.elapsed_time(y) for x, y in ev)
 print(json.dumps({"ms_med": ts[len(ts) // 2], "ms_best": ts[0]}))
 ''' % str(ROOT)
-libs = sys.argv[1:3]
-rows = int(sys.argv[3]) if len(sys.argv) > 3 else 100_000_000
+libs = [a for a in sys.argv[1:] if a.endswith(".so")]
+rows = next((int(a) for a in sys.argv[1:] if a.isdigit()), 100_000_000)
 res = {l: [] for l in libs}
 for rep in range(4):
     for l in libs:

@@ -52,6 +52,15 @@ class OracleEngine:
             st[i] = N.LO_NUM_INTEGER if (np.isfinite(v) and v.is_integer()) else N.LO_NUM_FLOAT
         return vals, st
 
+    def parse_number_packed(self, chars, offsets):
+        raw = bytes(chars)
+        cells = [raw[int(offsets[i]):int(offsets[i + 1])].decode("utf-8") for i in range(len(offsets) - 1)]
+        return self.parse_number_host(cells)
+
+    def value_counts_str_packed(self, chars, offsets):
+        raw = bytes(chars)
+        return self.value_counts_str_host([raw[int(offsets[i]):int(offsets[i + 1])] for i in range(len(offsets) - 1)])
+
     def minmax_cast_host(self, cols):
         mins, maxs, cnt = [], [], []
         for c in cols:

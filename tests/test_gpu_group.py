@@ -52,6 +52,11 @@ def _worker(rank, world, port, merge, ret):
         c = sh.project_cast_hist(table, cols, 256, lo4, hi4, out=out)
         if sh.has_result:
             got["f64"].append(c.to_numpy())
+    # eight INDEPENDENT steps back to back: consecutive launches may overlap (programmatic dependent launch, alternating
+    # accumulate matrices); only the last result is read, everything in between is in flight together
+    for _ in range(8):
+        c = sh.project_cast_hist(table, cols, 256, lo4, hi4, out=out, independent=True)
+    got["f64_overlap"] = c.to_numpy() if sh.has_result else None
     got["f64_bcast"] = sh.project_cast_hist(table, cols, 10, lo4, hi4, bcast=True).to_numpy()
     got["sums"] = [out.checksum(j) for j in range(4)]
     # range pre-pass over all shards (always delivered everywhere)
@@ -59,6 +64,9 @@ def _worker(rank, world, port, merge, ret):
     # u8: 300 columns x 256 bins = 76 800 counts -> the root's epilogue is its own multi-CTA launch
     t8 = sh.table("u8", 400_003, 300).fill_synthetic(3, SEED)
     got["u8"] = [sh.hist_u8_cols(t8, range(300), bcast=True).to_numpy() for _ in range(3)][-1]
+    for _ in range(5):
+        c8 = sh.hist_u8_cols(t8, range(300), bcast=True, independent=True)
+    got["u8_overlap"] = c8.to_numpy()
     # a shard with no rows still takes part in the step (world 3: 40 rows -> cuts at 0, 0, 32)
     tiny = sh.table("f64", 40, 2).fill_synthetic(1, SEED)
     got["tiny"] = sh.project_cast_hist(tiny, [1, 0], 16, lo4[:2], hi4[:2], bcast=True).to_numpy()
@@ -113,6 +121,7 @@ def _check(res, world, merge):
     assert len(res[0]["f64"]) == 5
     for c in res[0]["f64"]:                     # every step (both buffers, re-zeroed in between) is the exact merge
         np.testing.assert_array_equal(c, exp)
+    np.testing.assert_array_equal(res[0]["f64_overlap"], exp)
     total = [0] * 4
     for r in range(world):
         np.testing.assert_array_equal(res[r]["f64_bcast"], exp10)        # all-reduce semantics: every rank has it
@@ -129,6 +138,7 @@ def _check(res, world, merge):
     expt, _ = cport.synth_project_cast_hist(1, SEED, 0, 40, -1000.0, 1000.0, [1, 0], 16, lo4[:2], hi4[:2])
     for r in range(world):
         np.testing.assert_array_equal(res[r]["u8"], exp8)
+        np.testing.assert_array_equal(res[r]["u8_overlap"], exp8)
         np.testing.assert_array_equal(res[r]["tiny"], expt)
         assert res[r]["host_out_ok"]
     np.testing.assert_array_equal(res[0]["host_counts"], exp)
