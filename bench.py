@@ -275,6 +275,102 @@ def run_reference_arm(args) -> None:
 
 
 # ======================================================================================================
+# executor level: the reference's three operator classes on an in-process collection
+# ======================================================================================================
+def run_executor_e2e(engine, rows: int, with_cpu: bool) -> dict:
+    """rows/s through ``DataType.convert_existent_file`` ("number": text -> binary64 on the GPU),
+    ``Histogram.create_file`` (exact value counts = the reference's $group; and the binned extension, cold then warm
+    from the HBM-resident copy) and ``Projection.create`` (castTo float32), on a ``rows``-row collection held by the
+    in-process columnar store — the call a user of the reference's classes makes, host documents in, host documents
+    out.  ``reference_like``: the reference's own per-document algorithm (oracle/rsem.py restatement of
+    data_type_update.py:15-45 and a Counter group-by) on a 200k-row sample, single thread as the reference runs it."""
+    import pyarrow as pa
+    import pyarrow.compute as pc
+    from learningorchestra_b200 import utils
+    from learningorchestra_b200.column_store import ColumnarDatabase, TextColumn
+    from learningorchestra_b200.data_type_update import DataType
+    from learningorchestra_b200.histogram import Histogram
+    from learningorchestra_b200.projection import Projection
+
+    rng = np.random.default_rng(SEED)
+    t0 = time.perf_counter()
+    fare = np.round(rng.uniform(0, 600, rows), 4)
+    age = np.where(rng.random(rows) < 0.2, np.nan, np.round(rng.uniform(0, 90, rows), 1))
+    pclass = rng.integers(1, 4, rows)
+    sib = rng.integers(0, 9, rows)
+    text = {
+        "Fare": pc.cast(pa.array(fare), pa.large_string()),
+        "Age": pc.fill_null(pc.cast(pa.array(age, from_pandas=True), pa.large_string()), ""),       # blanks, as the CSV has them
+        "Pclass": pc.cast(pa.array(pclass), pa.large_string()),
+        "SibSp": pc.cast(pa.array(sib), pa.large_string()),
+        "Embarked": pa.array(np.array(["S", "C", "Q", ""])[rng.integers(0, 4, rows)], type=pa.large_string()),
+    }
+    db = ColumnarDatabase()
+    db.ingest_columns("big", {k: TextColumn(v) for k, v in text.items()})
+    build_s = time.perf_counter() - t0
+    out = {"rows": rows, "store": "column_store.ColumnarDatabase (Arrow text columns, as POST /files leaves them)",
+           "build_s": build_s}
+
+    def timed(fn):
+        a = time.perf_counter()
+        fn()
+        return time.perf_counter() - a
+
+    def cast():
+        job = DataType(db, utils.DataTypeMetadata(db), engine=engine)
+        job.convert_existent_file("big", {"Fare": "number", "Age": "number", "Pclass": "number", "SibSp": "number"})
+        job.wait(600)
+    dt = timed(cast)
+    out["datatype_number"] = {"fields": 4, "seconds": dt, "rows_per_s": rows / dt, "cells_per_s": 4 * rows / dt}
+
+    def counts(name, fields):
+        job = Histogram(db, utils.HistogramMetadata(db), engine=engine)
+        job.create_file("big", name, list(fields))
+        job.wait(600)
+    dt = timed(lambda: counts("big_h1", ["Pclass", "Embarked", "Age"]))
+    out["histogram_value_counts"] = {"fields": 3, "seconds": dt, "rows_per_s": rows / dt}
+
+    def binned(name):
+        job = Histogram(db, utils.HistogramMetadata(db), engine=engine)
+        job.create_file("big", name, ["Fare", "Age", "Pclass", "SibSp"], bins=64)
+        job.wait(600)
+    dt_cold = timed(lambda: binned("big_b1"))
+    dt_warm = timed(lambda: binned("big_b2"))
+    out["histogram_binned"] = {"fields": 4, "bins": 64, "cold_seconds": dt_cold, "warm_seconds": dt_warm,
+                               "cold_rows_per_s": rows / dt_cold, "warm_rows_per_s": rows / dt_warm,
+                               "note": "cold builds the HBM-resident copy of the 4 columns; warm reuses it"}
+
+    def project():
+        job = Projection(utils.ProjectionMetadata(db), engine)
+        job.create("big", "big_p", ["Fare", "Age"], "mongodb://h/database.big?r", "mongodb://h/database.big_p?r", cast_to="float32")
+        job.wait(600)
+    dt = timed(project)
+    out["projection_cast_float32"] = {"fields": 2, "seconds": dt, "rows_per_s": rows / dt}
+    meta = db.find_one("big_b2", {"_id": 0})
+    out["finished_flags_ok"] = bool(meta and meta.get("finished")) and bool(db.find_one("big_p", {"_id": 0}).get("finished"))
+    if with_cpu:
+        from collections import Counter
+        from oracle import rsem
+        n = min(rows, 200_000)
+        docs = [{"_id": i + 1, "Fare": a, "Age": b, "Pclass": c, "SibSp": d} for i, (a, b, c, d) in enumerate(zip(
+            text["Fare"].slice(0, n).to_pylist(), text["Age"].slice(0, n).to_pylist(), text["Pclass"].slice(0, n).to_pylist(),
+            text["SibSp"].slice(0, n).to_pylist()))]
+        a = time.perf_counter()
+        for f in ("Fare", "Age", "Pclass", "SibSp"):
+            rsem.convert_field(docs, f, "number")
+        dt = time.perf_counter() - a
+        a = time.perf_counter()
+        for f in ("Pclass", "Age"):
+            Counter(d[f] for d in docs)
+        dh = time.perf_counter() - a
+        out["reference_like"] = {"sample_rows": n, "threads": 1, "datatype_number_rows_per_s": n / dt,
+                                 "histogram_2_fields_rows_per_s": n / dh,
+                                 "note": "oracle/rsem.py per-document loop over in-memory dicts; flatters the reference: no "
+                                         "MongoDB round trip per document (data_type_update.py:45), no mongod $group scan"}
+    return out
+
+
+# ======================================================================================================
 # GPU arm
 # ======================================================================================================
 def _claim_stdout() -> int:
@@ -521,6 +617,15 @@ def run_gpu(args) -> int:
         alg_bytes = W["bytes_per_elem"] * k * nrows
         achieved = alg_bytes / (kernel_ms_avg * 1e-3) / 1e9
         cpu = run_cpu_baseline(w, total_rows, ncols, args.cpu_rows) if world == 1 and not args.no_cpu else None
+        executor = None
+        if world == 1 and w == "s100" and args.executor_rows > 0:
+            try:
+                table.free()
+                if out is not None:
+                    out.free()
+                executor = run_executor_e2e(eng, args.executor_rows, not args.no_cpu)
+            except Exception as exc:          # noqa: BLE001  (reported, never fatal for the headline line)
+                executor = {"error": repr(exc)}
         gb_in = nrows * k * (1 if w == "m" else 8) / 1e9
         line = {
             "metric": METRIC, "value": total_rows * args.steps / (elapsed_ms * 1e-3), "unit": "rows/s",
@@ -551,6 +656,8 @@ def run_gpu(args) -> int:
         }
         if cpu:
             line["cpu_baseline"] = cpu
+        if executor:
+            line["e2e_executor"] = executor
         tr = ROOT / "profiles" / "traffic.json"
         if tr.exists():
             try:
@@ -591,6 +698,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--executor-rows", type=int, default=10_000_000,
+                    help="rows of the in-process collection for the executor-level numbers (s100 at N = 1; 0 = skip)")
     ap.add_argument("--no-overlap", action="store_true",
                     help="serialise consecutive steps completely (no programmatic dependent launch between them)")
     ap.add_argument("--merge", default="auto", choices=["auto", "nccl", "p2p", "peer"],

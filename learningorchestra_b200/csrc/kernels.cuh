@@ -82,17 +82,6 @@ struct ColsU8 {
     int32_t col[kMaxColsU8];
 };
 
-// blockIdx -> (projected column, row range).  Two segments per column: `tiles_a` tiles of `batches_a` pipeline
-// batches each cover rows [0, tiles_a * rows(batches_a)), then `tiles_b` SHORT tiles of `batches_b` batches cover the
-// rest.  All segment-A blocks come first in blockIdx (= dispatch) order, so the last wave of the grid is made of short
-// tiles and the tail during which the machine drains is a fraction of a full tile (the 12.5 M-row shard of the
-// 8-GPU run lost 4.6 % to a 23rd wave that was 5 % full).  rows(b) = b * kPfBatch * kThreads * kVec.
-struct TileMap {
-    unsigned tiles_a, tiles_b;     // tiles per column in each segment (tiles_b may be 0)
-    unsigned blocks_a;             // k * tiles_a
-    int      batches_a, batches_b; // pipeline batches per tile: even, 2 .. kPfBatches
-};
-
 // One step of the multi-GPU histogram merge, executed INSIDE the streaming kernel (loexec.cu: lo_group_*).
 // Every device accumulates into its own `local` matrix; the CTA that finishes the last tile of a column pushes
 // that column's bins into the root GPU's `shared` matrix (system-scope RED.64 over NVLink / peer mapping), the CTA
@@ -273,7 +262,8 @@ __device__ __forceinline__ void fold_and_flush(uint32_t *smem, int rows, int nbi
     __syncthreads();
     if ((int)threadIdx.x < nbins) {
         uint32_t c = folded[threadIdx.x];
-        if (c) atomicAdd(counts + threadIdx.x, (unsigned long long)c);
+        // fire-and-forget reduction (RED, not an ATOM whose return value would have to come back before the CTA retires)
+        if (c) asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" :: "l"(counts + threadIdx.x), "l"((unsigned long long)c) : "memory");
     }
 }
 
@@ -377,7 +367,8 @@ __device__ __forceinline__ void group_finish_column(const GroupStep &G, unsigned
         unsigned long long *src = G.local + (long long)j * nb + b;
         const unsigned long long c = ld_relaxed_gpu(src);
         if (c) {
-            atomicAdd_system(G.shared + (long long)j * nb + b, c);     // the owner's L2 performs the reduction
+            // the owner's L2 performs the reduction
+            asm volatile("red.relaxed.sys.global.add.u64 [%0], %1;" :: "l"(G.shared + (long long)j * nb + b), "l"(c) : "memory");
             *src = 0ull;                                               // local matrix is clean for the next step
         }
     }
@@ -411,34 +402,15 @@ template <int OUT, bool HIST, bool ALIGNED, bool FASTDIV>
 __global__ void __launch_bounds__(kThreads, LO_MIN_CTAS)
 k_project_cast_hist(const char *__restrict__ in_base, long long in_pitch,
                     char *__restrict__ out_base, long long out_pitch,
-                    long long nrows, unsigned long long *__restrict__ counts,
-                    const __grid_constant__ ColsF64 P, const __grid_constant__ TileMap M,
-                    const __grid_constant__ GroupStep G) {
+                    long long nrows, unsigned tiles_per_col, unsigned long long *__restrict__ counts,
+                    const __grid_constant__ ColsF64 P, const __grid_constant__ GroupStep G) {
     extern __shared__ uint32_t smem[];
     // overlapped steps: the next launch may start filling SMs as soon as every CTA of this one is resident
     if (G.overlap) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    // blockIdx -> (column j, rows [r0, r0 + n)): full-size tiles first, the short tiles of the tapered tail last
-    unsigned j, tile;
-    int nbatches;
-    long long r0;
-    if (blockIdx.x < M.blocks_a) {
-        j = blockIdx.x / M.tiles_a;
-        tile = blockIdx.x - j * M.tiles_a;
-        nbatches = M.batches_a;
-#ifdef LO_STATIC_TILES          // A/B build: compile-time pipeline depth, as in round 1
-        nbatches = kPfBatches;
-#endif
-        r0 = (long long)tile * (M.batches_a * (kPfBatch * kThreads * kVec));
-    } else {
-        const unsigned b = blockIdx.x - M.blocks_a;
-        j = b / M.tiles_b;
-        tile = b - j * M.tiles_b;
-        nbatches = M.batches_b;
-        r0 = (long long)M.tiles_a * (M.batches_a * (kPfBatch * kThreads * kVec)) +
-             (long long)tile * (M.batches_b * (kPfBatch * kThreads * kVec));
-    }
-    const long long tile_rows = (long long)nbatches * (kPfBatch * kThreads * kVec);
-    const long long n = min(tile_rows, nrows - r0);   // rows in this tile (> 0)
+    const unsigned j    = blockIdx.x / tiles_per_col;
+    const unsigned tile = blockIdx.x - j * tiles_per_col;
+    const long long r0  = (long long)tile * kTileRows;
+    const long long n   = min((long long)kTileRows, nrows - r0);   // rows in this tile (> 0)
 
     const double *in = reinterpret_cast<const double *>(in_base + (long long)P.col[j] * in_pitch) + r0;
     float  *out32 = nullptr;
@@ -458,8 +430,8 @@ k_project_cast_hist(const char *__restrict__ in_base, long long in_pitch,
         // a thread only touches its own words until fold_and_flush: no barrier needed here
     }
 
-    if (ALIGNED && n == tile_rows) {
-        // full tile: no bounds checks, register-pipelined loads.
+    if (ALIGNED && n == kTileRows) {
+        // full tile (all but the last tile of a column): no bounds checks, register-pipelined loads.
         // vector index of (batch b, slot u) = (b*kPfBatch + u)*kThreads + tid  ->  warp-contiguous 1 KiB
         double v[kPfBuf][kPfBatch][4];
         const double *src = in + (long long)threadIdx.x * kVec;
@@ -469,12 +441,12 @@ k_project_cast_hist(const char *__restrict__ in_base, long long in_pitch,
             for (int u = 0; u < kPfBatch; ++u)
                 ldg256_stream(src + (long long)(pb * kPfBatch + u) * kThreads * kVec, v[pb][u]);
 #pragma unroll 1
-        for (int b0 = 0; b0 < nbatches; b0 += kPfBuf) {
+        for (int b0 = 0; b0 < kPfBatches; b0 += kPfBuf) {
 #pragma unroll
             for (int s = 0; s < kPfBuf; ++s) {
                 const int b  = b0 + s;                 // batch being processed, lives in buffer s
                 const int nb = b + kPfBuf - 1;         // batch to fetch, into buffer (s + kPfBuf - 1) % kPfBuf
-                if (nb < nbatches) {
+                if (nb < kPfBatches) {
 #pragma unroll
                     for (int u = 0; u < kPfBatch; ++u)
                         ldg256_stream(src + (long long)(nb * kPfBatch + u) * kThreads * kVec, v[(s + kPfBuf - 1) % kPfBuf][u]);
@@ -552,7 +524,7 @@ k_project_cast_hist(const char *__restrict__ in_base, long long in_pitch,
             // multi-GPU merge riding on the flush: accumulate on this device, the column's last tile pushes to the root
             group_wait_generation(G);
             fold_and_flush(smem, rows, P.nbins, G.local + (long long)j * P.nbins);
-            group_finish_column(G, j, P.nbins, P.k, M.tiles_a + M.tiles_b, smem);
+            group_finish_column(G, j, P.nbins, P.k, tiles_per_col, smem);
         }
     }
 }
@@ -958,20 +930,45 @@ __global__ void k_fill_u8_mnist(uint8_t *base, long long pitch, long long nrows,
 // ---------------------------------------------------------------------------------------------
 // multi-GPU merge: the launches that are NOT the streaming kernel
 // ---------------------------------------------------------------------------------------------
-// root epilogue as its own multi-CTA launch, for count matrices too large for one CTA to move in a few
-// microseconds (config M: 784 x 256 counts = 1.5 MiB).  Every CTA waits for the W arrivals itself, moves its slice,
-// and the CTA that finishes last tells the peers.
+// Merge of a LARGE count matrix (config M: 784 x 256 counts = 1.5 MiB) as its own launch after a plain streaming
+// kernel that accumulated into G.local: moving that much through one CTA (or paying a ticket + fence per streaming
+// CTA — 13 k CTAs of ~10 us each for config M) costs more than a second launch.  grid <= SM count, so every CTA is
+// resident and CTAs may wait on each other through global memory.  Phase 1: each CTA pushes its slice of the local
+// matrix into the root's (system-scope RED.64) and re-zeroes it; the last one arrives.  Phase 2 (root): every CTA
+// waits for the W arrivals itself, moves its slice of the merged matrix out and re-zeroes it; the last one tells
+// the peers.
 __global__ void __launch_bounds__(256)
-k_group_root_epilogue(const __grid_constant__ GroupStep G, int n) {
+k_group_merge_big(const __grid_constant__ GroupStep G, int n) {
     __shared__ int ok, last;
-    if (threadIdx.x == 0) ok = wait_flag_ge(G.arrived, G.arrive_target, G.timeout_ns, G.timed_out) ? 1 : 0;
+    const int first = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    if (threadIdx.x == 0 && G.clean) wait_flag_ge(G.clean, G.clean_target, G.timeout_ns, G.timed_out);
     __syncthreads();
-    if (ok) group_root_epilogue(G, n, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, false);
+    for (int i = first; i < n; i += stride) {
+        const unsigned long long c = ld_relaxed_gpu(G.local + i);
+        if (c) {
+            asm volatile("red.relaxed.sys.global.add.u64 [%0], %1;" :: "l"(G.shared + i), "l"(c) : "memory");
+            G.local[i] = 0ull;
+        }
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence_system();
-        last = atomicAdd(G.done_ticket, 1u) == gridDim.x - 1u;
-        if (last) { *G.done_ticket = 0u; __threadfence_system(); }
+        if (atomicAdd(G.done_ticket, 1u) == gridDim.x - 1u) {
+            *G.done_ticket = 0u;
+            __threadfence_system();
+            red_release_sys_add(G.arrived, 1ull);
+            asm volatile("red.release.gpu.global.add.u64 [%0], %1;" :: "l"(G.gen), "l"(1ull) : "memory");
+        }
+        ok = G.is_root ? (wait_flag_ge(G.arrived, G.arrive_target, G.timeout_ns, G.timed_out) ? 1 : 0) : -1;
+    }
+    __syncthreads();
+    if (ok < 0) return;                                   // not the root: done
+    if (ok) group_root_epilogue(G, n, first, stride, false);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        last = atomicAdd(G.col_ticket, 1u) == gridDim.x - 1u;
+        if (last) { *G.col_ticket = 0u; __threadfence_system(); }
     }
     __syncthreads();
     if (last && (int)threadIdx.x < G.npeers) red_release_sys_add(G.peer_clean[threadIdx.x], 1ull);

@@ -182,40 +182,6 @@ int configure_kernels() {
     return LO_OK;
 }
 
-// blockIdx -> tile map of one launch (kernels.cuh TileMap).  A tapered tail can be requested: the last `tail_waves`
-// waves' worth of rows is cut into short tiles (`tail_batches` pipeline batches instead of kPfBatches), so the drain
-// at the end of the launch costs a fraction of a full tile's time.  MEASURED (scripts/tile_sweep.py,
-// profiles/r02_tile_sweep.json): it does not pay — at 12.5 M rows x 32 (the 8-GPU shard) every taper is equal or
-// slower than uniform tiles (0.752 ms vs 0.752 - 0.764), at 100 M rows 2 % slower: the ~30 us a launch loses against
-// the steady-state rate is not wave quantisation.  So the default is no taper; LOEXEC_TAIL_BATCHES / LOEXEC_TAIL_WAVES
-// remain as measurement knobs.
-lo::TileMap make_tilemap(const lo_ctx *ctx, int64_t nrows, int32_t k) {
-    constexpr int64_t kBatchRows = (int64_t)lo::kPfBatch * lo::kThreads * lo::kVec;     // 5120
-    lo::TileMap M;
-    M.batches_a = lo::kPfBatches;
-    M.batches_b = lo::kPfBatches;
-    M.tiles_a = (unsigned)((nrows + lo::kTileRows - 1) / lo::kTileRows);
-    M.tiles_b = 0;
-    int tail_batches = 0;
-    double tail_waves = 1.0;
-    if (const char *e = getenv("LOEXEC_TAIL_BATCHES")) tail_batches = atoi(e);
-    if (const char *e = getenv("LOEXEC_TAIL_WAVES")) tail_waves = atof(e);
-    const int64_t slots = (int64_t)ctx->sm_count * LO_MIN_CTAS;
-    const int64_t full_tiles = nrows / lo::kTileRows;           // per column
-    if (tail_batches >= 2 && tail_batches < lo::kPfBatches && tail_batches % lo::kPfBuf == 0 && tail_waves > 0.0 &&
-        full_tiles * k > slots) {
-        int64_t tail_tiles = (int64_t)std::ceil(tail_waves * (double)slots / (double)k);   // full tiles per column -> short
-        tail_tiles = std::min(std::max<int64_t>(tail_tiles, 1), full_tiles);
-        const int64_t rows_a = (full_tiles - tail_tiles) * lo::kTileRows;
-        const int64_t rows_b = nrows - rows_a;
-        M.tiles_a = (unsigned)(full_tiles - tail_tiles);
-        M.batches_b = tail_batches;
-        M.tiles_b = (unsigned)((rows_b + tail_batches * kBatchRows - 1) / (tail_batches * kBatchRows));
-    }
-    M.blocks_a = M.tiles_a * (unsigned)k;
-    return M;
-}
-
 const lo::GroupStep kNoGroup = {};     // mode 0
 
 // <<<>>> with one optional launch attribute: programmatic stream serialization lets THIS launch's CTAs start as soon
@@ -259,25 +225,28 @@ int launch_f64(lo_ctx *ctx, const lo_table *in, const lo_table *out, int32_t out
         const int64_t done = (int64_t)full_tiles * lo::kTileRows;
         if (done == in->nrows) return LO_OK;
         // the remaining rows of every column: one ragged tile each, through the regular kernel on a row-offset view
-        const lo::TileMap M1 = {1u, 0u, (unsigned)P.k, lo::kPfBatches, lo::kPfBatches};
         const char *ib = in->base + done * 8;
         char *ob = out ? out->base + done * (int64_t)dtype_size(out->dtype) + (int64_t)out_col0 * out->pitch : nullptr;
         if (fast) lo::k_project_cast_hist<OUT, HIST, true, true><<<(unsigned)P.k, lo::kThreads, smem, s>>>(
-                      ib, in->pitch, ob, out_pitch, in->nrows - done, counts, P, M1, kNoGroup);
+                      ib, in->pitch, ob, out_pitch, in->nrows - done, 1u, counts, P, kNoGroup);
         else      lo::k_project_cast_hist<OUT, HIST, true, false><<<(unsigned)P.k, lo::kThreads, smem, s>>>(
-                      ib, in->pitch, ob, out_pitch, in->nrows - done, counts, P, M1, kNoGroup);
+                      ib, in->pitch, ob, out_pitch, in->nrows - done, 1u, counts, P, kNoGroup);
         LO_CUDA(cudaGetLastError());
         ctx->launches.fetch_add(1, std::memory_order_relaxed);
         return LO_OK;
     }
-    const lo::TileMap M = make_tilemap(ctx, in->nrows, P.k);
-    const unsigned long long blocks = ((unsigned long long)M.tiles_a + M.tiles_b) * (unsigned)P.k;
+    // one tile (kTileRows rows of one projected column) per CTA.  A tapered tail — the last wave cut into short
+    // tiles — was built and measured in round 2 (profiles/r02_tile_sweep.json): equal or slower at every shard size
+    // (12.5 M rows x 32: 0.752 ms uniform vs 0.752 - 0.764 tapered; 100 M: 2 % slower), and the runtime tile shape cost
+    // the uniform case 3 % (5.71 vs 5.53 ms, same box, scripts/ab_libs.py), so tiles are compile-time uniform again.
+    const unsigned tiles_per_col = (unsigned)((in->nrows + lo::kTileRows - 1) / lo::kTileRows);
+    const unsigned long long blocks = (unsigned long long)tiles_per_col * (unsigned)P.k;
     if (blocks > 0x7fffffffull) return fail(LO_ERR_INVALID, "table too large for one launch (%llu tiles)", blocks);
     const char *ib = in->base;
     const long long ip = in->pitch, nr = in->nrows;
 #define LO_LAUNCH(AL, FD)                                                                                        \
     LO_CUDA(launch_kernel(lo::k_project_cast_hist<OUT, HIST, AL, FD>, (unsigned)blocks, lo::kThreads, smem, s,    \
-                          G.overlap != 0, ib, ip, out_base, out_pitch, nr, counts, P, M, G))
+                          G.overlap != 0, ib, ip, out_base, out_pitch, nr, tiles_per_col, counts, P, G))
     if (aligned) { if (fast) LO_LAUNCH(true, true); else LO_LAUNCH(true, false); }
     else         { if (fast) LO_LAUNCH(false, true); else LO_LAUNCH(false, false); }
 #undef LO_LAUNCH

@@ -14,6 +14,7 @@ done
 if [[ "$*" == *sweep* ]]; then
   timeout 600 python scripts/tile_sweep.py 2>&1 | tail -50
 fi
+if [[ "$*" == *ab* ]]; then timeout 600 python scripts/ab_libs.py $PWD/learningorchestra_b200/lib/libloexec.so $PWD/learningorchestra_b200/lib/libloexec_r1.so 2>&1 | tail -4; timeout 600 python scripts/ab_libs.py $PWD/learningorchestra_b200/lib/libloexec.so $PWD/learningorchestra_b200/lib/libloexec_r1.so 12500000 2>&1 | tail -2; fi
 if [[ "$*" != *noncu* ]]; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv \
       --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu > gpurun_out/ncu_launch_$TAG.log 2>&1

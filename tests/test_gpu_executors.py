@@ -328,3 +328,81 @@ def test_builder_front_end_serves_resident_columns(engine):
     assert host.equals(dev)
     assert {"Age", "Fare", "Survived"} <= set(engine.resident.ensure(db, "titanic", ["Age"]).fields)
     engine.resident.clear()
+
+
+# ---- the columnar store on the real engine (tests/test_column_store_cpu.py runs the same flow on the stand-in) ----------
+def test_columnar_store_titanic_flow_matches_reference_execution(engine, tmp_path):
+    import csv
+    import io
+    from learningorchestra_b200.column_store import ColumnarDatabase, NumberColumn
+    g = json.loads((GOLD / "titanic_shaped_input.json").read_text())
+    buf = io.StringIO()
+    w = csv.writer(buf, lineterminator="\n")
+    w.writerow(g["headers"]); w.writerows(g["rows"])
+    path = tmp_path / "titanic.csv"
+    path.write_text(buf.getvalue())
+    db = ColumnarDatabase()
+    assert db.ingest_csv("titanic", str(path)) == 891
+    gold = json.loads((GOLD / "reference_datatype_number.json").read_text())
+    job = DataType(db, utils.DataTypeMetadata(db), engine=engine)
+    job.convert_existent_file("titanic", {f: "number" for f in gold["fields"]})
+    job.wait(120)
+    assert db.find_one("titanic", {"_id": 0})["finished"] is True
+    assert all(isinstance(db.column("titanic", f), NumberColumn) for f in gold["fields"])
+    got = [[d["_id"]] + [d[f] for f in gold["fields"]] for d in db.find("titanic", {}) if d["_id"] != 0]
+    for a, b in zip(got, gold["rows"]):
+        assert all(type(x) is type(y) and x == y for x, y in zip(a, b)), (a, b)
+    hg = json.loads((GOLD / "reference_histogram.json").read_text())
+    hist = Histogram(db, utils.HistogramMetadata(db), engine=engine)
+    hist.create_file("titanic", "titanic_hist", list(hg["fields"]))
+    hist.wait(120)
+    ours = [d for d in db.find("titanic_hist", {}) if d["_id"] != 0]
+    ref = [d for d in hg["documents"] if d["_id"] != 0]
+    for mine, theirs, f in zip(ours, ref, hg["fields"]):
+        assert rsem.normalise_group_result(mine[f]) == rsem.normalise_group_result(theirs[f]), f
+    # binned extension from the HBM-resident copy, constant and all-null columns included (range widened, not an error)
+    n = db.nrows("titanic")
+    db.set_column("titanic", "Const", NumberColumn(np.full(n, 7.0), np.ones(n, bool), np.ones(n, bool)))
+    db.set_column("titanic", "Nulls", NumberColumn(np.full(n, np.nan), np.zeros(n, bool)))
+    hist = Histogram(db, utils.HistogramMetadata(db), engine=engine)
+    hist.create_file("titanic", "titanic_bins", ["Age", "Const", "Nulls"], bins=10)
+    hist.wait(120)
+    docs = {list(d)[0]: d[list(d)[0]] for d in db.find("titanic_bins", {}) if d["_id"] != 0}
+    age = np.array([r[3] if r[3] is not None else np.nan for r in gold["rows"]], dtype=np.float64)
+    lo, hi = bn.auto_range([np.nanmin(age).astype(np.float32)], [np.nanmax(age).astype(np.float32)], [int(np.isfinite(age).sum())])
+    assert docs["Age"]["counts"] == bn.hist_f32(bn.cast_f64_f32(age), lo[0], hi[0], 10).tolist()
+    assert docs["Const"]["range"] == [6.5, 7.5] and sum(docs["Const"]["counts"]) == n and docs["Const"]["counts"][5] == n
+    assert docs["Nulls"]["range"] == [0.0, 1.0] and sum(docs["Nulls"]["counts"]) == 0
+    # castTo projection through the resident slabs
+    proj = Projection(utils.ProjectionMetadata(db), engine)
+    proj.create("titanic", "titanic_f32", ["Fare", "Age"], "mongodb://h/database.titanic?r", "mongodb://h/database.titanic_f32?r", cast_to="float32")
+    proj.wait(120)
+    fare = np.array([r[4] for r in gold["rows"]], dtype=np.float64)
+    gotf = [d["Fare"] for d in db.find("titanic_f32", {}) if d["_id"] != 0]
+    assert gotf == [float(x) for x in bn.cast_f64_f32(fare)]
+
+
+def test_columnar_store_large_text_column_parse(engine):
+    """2 M cells straight from Arrow buffers to the GPU parser: values / int-collapse equal CPython's float() on a sample."""
+    import pyarrow as pa
+    import pyarrow.compute as pc
+    from learningorchestra_b200.column_store import ColumnarDatabase, TextColumn
+    rng = np.random.default_rng(5)
+    n = 2_000_000
+    vals = np.where(rng.random(n) < 0.5, np.round(rng.uniform(-1e4, 1e4, n), 3), rng.integers(-10 ** 9, 10 ** 9, n).astype(np.float64))
+    text = pc.cast(pa.array(vals), pa.large_string())
+    db = ColumnarDatabase()
+    db.ingest_columns("big", {"x": TextColumn(text)})
+    job = DataType(db, utils.DataTypeMetadata(db), engine=engine)
+    job.convert_existent_file("big", {"x": "number"})
+    job.wait(300)
+    col = db.column("big", "x")
+    cells = text.to_pylist()
+    for i in rng.integers(0, n, 5000):
+        w = float(cells[i])
+        assert col.values[i] == w and bool(col.is_int[i]) == w.is_integer(), (cells[i], col.values[i])
+    hist = Histogram(db, utils.HistogramMetadata(db), engine=engine)
+    hist.create_file("big", "big_h", ["x"])
+    hist.wait(300)
+    groups = db.find_one("big_h", {"_id": 1})["x"]
+    assert sum(g["count"] for g in groups) == n + 1            # + the metadata document under null

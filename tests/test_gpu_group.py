@@ -187,23 +187,3 @@ def test_local_group_over_all_visible_devices(built):
         assert tm["h2d_bytes"] == rows * 3 * 8 and sh.timeouts() == 0
         mins, maxs, cnt = sh.minmax_cast(table, cols)
         assert mins.shape == (3,) and (maxs >= mins).all() and int(cnt.sum()) > 0
-
-
-def test_tapered_tail_tiles_give_identical_results(built, monkeypatch):
-    """The short tiles of the last wave (TileMap) change nothing but the schedule: every (tail_batches, tail_waves)
-    combination, including none, gives the oracle's counts and output on a multi-wave table."""
-    from learningorchestra_b200.engine import Engine
-    from oracle import cport
-    rows, cols = 61440 * 12 + 12_345, list(range(32))
-    lo, hi = np.full(32, -1000.0, np.float32), np.full(32, 1000.0, np.float32)
-    exp, sums = cport.synth_project_cast_hist(1, SEED, 0, rows, -1000.0, 1000.0, cols, 256, lo, hi)
-    with Engine(0) as eng:
-        table = eng.table("f64", rows, 32).fill_synthetic(1, SEED)
-        out = eng.table("f32", rows, 32)
-        for tb, tw in [("0", "1"), ("2", "0.5"), ("4", "1"), ("6", "2.5"), ("10", "40")]:
-            monkeypatch.setenv("LOEXEC_TAIL_BATCHES", tb)
-            monkeypatch.setenv("LOEXEC_TAIL_WAVES", tw)
-            got = eng.project_cast_hist(table, cols, 256, lo, hi, out=out)
-            np.testing.assert_array_equal(got.to_numpy(), exp)
-            got.free()
-            assert [out.checksum(j) for j in range(32)] == [int(s) for s in sums]
