@@ -6,7 +6,8 @@ Layout (DESIGN.md):
   projection, data_type_update, histogram, utils, server
                    drop-in mirrors of the reference's service classes and REST routes
   columnar         documents <-> columns adapter;  table_cache: datasets resident in HBM
-  sharding         row-range shards across GPUs, NCCL all-reduce or peer-memory merge
+  column_store     the wrapper API over rows stored as columns (Arrow text / float64), CSV ingest
+  sharding         ShardedEngine: several GPUs behind the Engine methods (lo_group_* in the library)
 
 There is no CPU fallback: without libloexec.so and a B200 every compute entry raises LoexecError.
 """

@@ -5,6 +5,10 @@ routes, JSON keys, status codes, messages and GET-URI bodies of the reference:
   PATCH /fieldTypes    data_type_handler_image/server.py:40-90 200 / 406
   POST  /histograms    histogram_image/server.py:43-120        201 / 409 / 406
   GET   /files/<name>  database_api_image/server.py:52-80      paged reader (sorted by _id, limit <= 100)
+  POST  /files         database_api_image/server.py:19-49      CSV ingest (the producer of the table format): body
+                       {"datasetName", "datasetURI"}; 201 / 409 "duplicated dataset name" / 406 "invalid url"
+                       (utils.py:78-95).  Only file:// URIs and local paths are read (no network here); rows land as
+                       columns (column_store)
 
 Optional extension keys (absent from the reference, ignored by it): ``castTo``, ``bins``, ``range``.
 The gateway paths of ``krakend/krakend.json:143-365`` map 1:1 onto these routes.
@@ -62,6 +66,7 @@ class App:
             Rule("/fieldTypes", endpoint="datatype", methods=["PATCH"]),
             Rule("/histograms", endpoint="histogram", methods=["POST"]),
             Rule("/files/<filename>", endpoint="read", methods=["GET"]),
+            Rule("/files", endpoint="ingest", methods=["POST"]),
         ])
 
     # ---- POST /projections -----------------------------------------------------------------------------
@@ -130,6 +135,19 @@ class App:
         query = json.loads(request.args.get("query", "{}") or "{}")
         return _json({MESSAGE_RESULT: self.database.find_in_file(filename, query, skip, limit)}, HTTP_STATUS_CODE_SUCCESS)
 
+    # ---- POST /files (database_api_image/server.py:19-49; keys constants.py:17-18; messages utils.py:79-80) ------
+    def on_ingest(self, request):
+        body = request.get_json()
+        filename, url = body["datasetName"], body["datasetURI"]
+        if filename in self.database.get_filenames():
+            return _json({MESSAGE_RESULT: "duplicated dataset name"}, HTTP_STATUS_CODE_CONFLICT)
+        path = url[len("file://"):] if url.startswith("file://") else url
+        import os
+        if not hasattr(self.database, "ingest_csv") or not os.path.isfile(path):
+            return _json({MESSAGE_RESULT: "invalid url"}, HTTP_STATUS_CODE_NOT_ACCEPTABLE)
+        self.database.ingest_csv(filename, path, url=url)
+        return _json({MESSAGE_RESULT: f"{DATATYPE_URI_GET}{filename}?query={{}}&limit=10&skip=0"}, HTTP_STATUS_CODE_SUCCESS_CREATED)
+
     def _maybe_wait(self, job):
         if self.synchronous:
             try:
@@ -151,21 +169,27 @@ class App:
 
 
 def create_app(database: Database | None = None, engine=None, synchronous: bool = False) -> App:
-    return App(database or Database(), engine, synchronous)
+    if database is None:
+        from .column_store import ColumnarDatabase
+        database = ColumnarDatabase()
+    return App(database, engine, synchronous)
 
 
 def main() -> None:
     """``python -m learningorchestra_b200.server``: the three hot-path routes on one werkzeug dev server (the reference
     runs three Flask processes with ``app.run(host, port)``, e.g. ``projection_image/server.py:157-161``).
-    LOEXEC_HOST / LOEXEC_PORT / LOEXEC_DEVICE select the bind address and the GPU."""
+    LOEXEC_HOST / LOEXEC_PORT select the bind address; LOEXEC_DEVICES (e.g. "0,1,2,3"; default: every visible GPU)
+    the devices — with more than one, every binned histogram / castTo projection shards the resident table over them
+    (``sharding.open_engine`` -> ``lo_group_create_local``)."""
     import os
 
     from werkzeug.serving import run_simple
 
-    from .engine import Engine
+    from .sharding import open_engine
 
-    engine = Engine(int(os.environ.get("LOEXEC_DEVICE", "0")))          # fails loudly without a B200
-    app = create_app(Database(), engine)
+    devs = os.environ.get("LOEXEC_DEVICES") or os.environ.get("LOEXEC_DEVICE")
+    engine = open_engine([int(d) for d in devs.split(",")] if devs else None)       # fails loudly without a B200
+    app = create_app(None, engine)
     run_simple(os.environ.get("LOEXEC_HOST", "127.0.0.1"), int(os.environ.get("LOEXEC_PORT", "5001")), app, threaded=True)
 
 

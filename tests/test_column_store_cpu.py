@@ -167,3 +167,26 @@ def test_column_classification():
     assert isinstance(column_from_values([1, "a"]), ObjectColumn)
     assert isinstance(column_from_values([2 ** 60, 1]), ObjectColumn)
     assert isinstance(column_from_values([True, 1]), ObjectColumn) or column_from_values([True, 1]).to_pylist() == [True, 1]
+
+
+def test_rest_ingest_route_then_the_three_services(tmp_path):
+    """POST /files -> PATCH /fieldTypes -> POST /histograms -> GET /files: the Titanic-shaped flow over HTTP, keys /
+    codes / messages of database_api_image/server.py:19-49 and utils.py:78-95."""
+    from werkzeug.test import Client
+    from learningorchestra_b200 import server
+    g = _load("titanic_shaped_input.json")
+    path = tmp_path / "t.csv"
+    path.write_text(_csv_text(g["headers"], g["rows"]))
+    app = server.create_app(None, OracleEngine(), synchronous=True)
+    c = Client(app)
+    r = c.post("/files", json={"datasetName": "titanic", "datasetURI": f"file://{path}"})
+    assert r.status_code == 201 and r.get_json() == {"result": "/api/learningOrchestra/v1/dataset/titanic?query={}&limit=10&skip=0"}
+    assert c.post("/files", json={"datasetName": "titanic", "datasetURI": f"file://{path}"}).get_json() == {"result": "duplicated dataset name"}
+    r = c.post("/files", json={"datasetName": "nope", "datasetURI": "file:///does/not/exist.csv"})
+    assert r.status_code == 406 and r.get_json() == {"result": "invalid url"}
+    assert c.patch("/fieldTypes", json={"inputDatasetName": "titanic", "types": {"Age": "number", "Fare": "number"}}).status_code == 200
+    assert c.post("/histograms", json={"inputDatasetName": "titanic", "outputDatasetName": "h", "names": ["Age", "Sex"]}).status_code == 201
+    page = c.get("/files/titanic?limit=3&skip=0").get_json()["result"]
+    assert [d["_id"] for d in page] == [0, 1, 2] and page[0]["finished"] is True and isinstance(page[1]["Fare"], (int, float))
+    h = c.get("/files/h?limit=10").get_json()["result"]
+    assert [d["_id"] for d in h] == [0, 1, 2] and h[0]["finished"] is True
