@@ -47,6 +47,47 @@ def file_processor(database, filename, engine=None):
             engine.resident.release(resident)
 
 
+class DeviceFrame:
+    """The processed frame for a GPU consumer: the HBM-resident slabs themselves, no device->host copy.
+    ``columns[name]`` is a list of :class:`~learningorchestra_b200.engine.DeviceColumn` (one per shard: one element on a
+    single GPU) exposing ``__cuda_array_interface__`` — nulls are NaN in the slab; ``nulls[name]`` counts them.
+    Holds a lease on the resident dataset: call :meth:`release` (or use ``with``) when the consumer is done."""
+
+    def __init__(self, cache, data, fields):
+        self._cache, self._data = cache, data
+        self.fields = list(fields)
+        self.ids = data.ids
+        shards = getattr(data.table, "shards", [data.table])
+        self.columns = {f: [t.column_view(data.column[f], keepalive=self) for t in shards] for f in self.fields}
+        self.kinds = {f: data.kinds[data.column[f]] for f in self.fields}
+        self.nulls = {f: data.nulls[data.column[f]] for f in self.fields}
+
+    def release(self):
+        if self._data is not None:
+            self._cache.release(self._data)
+            self._data = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.release()
+
+
+def device_frame(database, filename, engine) -> DeviceFrame:
+    """``Builder.__file_processor``'s frame (data rows, metadata columns dropped) handed over ON THE DEVICE: the
+    numeric fields of the dataset as zero-copy views of the resident slabs (``builder_image/builder.py:172-194`` loads
+    the same frame into Spark).  Text fields are not part of it — use :func:`file_processor` for the host form."""
+    if getattr(database, "has_columns", lambda _f: False)(filename):
+        names = [f for f in database.column_names(filename) if f not in METADATA_FIELDS]
+        numeric = [f for f in names if getattr(database.column(filename, f), "kind", "") == "number"]
+    else:
+        names, rows = frame_fields(database, filename)
+        numeric = [f for f in names if rows and columnar.numeric_column([d.get(f) for d in rows]) is not None]
+    data = engine.resident.ensure(database, filename, numeric)
+    return DeviceFrame(engine.resident, data, numeric)
+
+
 def _frame(fields, rows, packed, resident):
     import numpy as np
     import pyarrow as pa

@@ -94,8 +94,11 @@ struct GroupStep {
     int is_root, npeers, epilogue_in_kernel;
     int overlap, pad_;                 // 1: launched with programmatic stream serialization: let the NEXT launch's CTAs
                                        //    take the SMs this one's tail leaves idle (LO_GROUP_INDEPENDENT)
-    unsigned long long *gen;           // steps of this parity whose pushes have completed on this device
+    unsigned long long *gen;           // steps of this parity that are COMPLETE on this device: pushed, and on the root
+                                       // also merged out (the root's own next push into `shared` must wait for that)
     unsigned long long gen_target;     // flush only once *gen >= gen_target (the step two launches back is done)
+    unsigned long long *epi_seq;       // root: number of finished epilogues; epilogues run in step order even when
+    unsigned long long step;           // their launches overlap, so `result` always ends up holding the LAST step
     unsigned long long *local;         // this device's accumulate matrix (zero at entry, left zero at exit)
     unsigned long long *shared;        // root's merge matrix of this step's parity (peer-mapped on the others)
     unsigned long long *arrived;       // root's arrival counter of this parity
@@ -309,6 +312,24 @@ __device__ __forceinline__ bool wait_flag_ge(const unsigned long long *flag, uns
     }
 }
 
+// root, one thread: epilogues of overlapped launches take their turn in step order
+__device__ __forceinline__ void epilogue_turn_wait(const GroupStep &G) {
+    unsigned long long v;
+    const unsigned long long t0 = globaltimer_ns();
+    for (;;) {
+        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(G.epi_seq) : "memory");
+        if (v >= G.step) return;
+        if (globaltimer_ns() - t0 > G.timeout_ns) { atomicAdd(G.timed_out, 1ull); return; }
+        __nanosleep(64);
+    }
+}
+// root, one thread, after the epilogue: this parity may be reused by the launch after next, the next epilogue may run
+__device__ __forceinline__ void epilogue_turn_done(const GroupStep &G) {
+    __threadfence();
+    asm volatile("red.release.gpu.global.add.u64 [%0], %1;" :: "l"(G.gen), "l"(1ull) : "memory");
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(G.epi_seq), "l"(G.step + 1ull) : "memory");
+}
+
 // root: all W devices have pushed -> move the merged matrix out, re-zero it, tell the peers.  One CTA (any size).
 __device__ __forceinline__ void group_root_epilogue(const GroupStep &G, int n, int first, int stride, bool signal) {
     for (int i = first; i < n; i += stride) {
@@ -380,15 +401,23 @@ __device__ __forceinline__ void group_finish_column(const GroupStep &G, unsigned
             *G.done_ticket = 0u;
             __threadfence_system();
             red_release_sys_add(G.arrived, 1ull);
-            // this parity's accumulate matrix and tickets are clean again: the launch after next may flush into them
-            asm volatile("red.release.gpu.global.add.u64 [%0], %1;" :: "l"(G.gen), "l"(1ull) : "memory");
+            // not the root: this parity's accumulate matrix and tickets are clean again, the launch after next may
+            // flush into them.  The root says so only after its epilogue: its own next push goes into `shared` too.
+            if (!G.is_root) asm volatile("red.release.gpu.global.add.u64 [%0], %1;" :: "l"(G.gen), "l"(1ull) : "memory");
         }
-        *sflag = (last && G.is_root && G.epilogue_in_kernel) ? 2u : 0u;
-        if (*sflag == 2u && !wait_flag_ge(G.arrived, G.arrive_target, G.timeout_ns, G.timed_out)) *sflag = 3u;
+        *sflag = (last && G.is_root) ? 2u : 0u;
+        if (*sflag == 2u) {
+            epilogue_turn_wait(G);
+            if (!wait_flag_ge(G.arrived, G.arrive_target, G.timeout_ns, G.timed_out)) *sflag = 3u;
+        }
     }
     __syncthreads();
     if (*sflag == 2u) group_root_epilogue(G, k * nb, threadIdx.x, blockDim.x, true);
     else if (*sflag == 3u && (int)threadIdx.x < G.npeers) red_release_sys_add(G.peer_clean[threadIdx.x], 1ull);
+    if (*sflag >= 2u) {
+        __syncthreads();
+        if (threadIdx.x == 0) epilogue_turn_done(G);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -957,7 +986,7 @@ k_group_merge_big(const __grid_constant__ GroupStep G, int n) {
             *G.done_ticket = 0u;
             __threadfence_system();
             red_release_sys_add(G.arrived, 1ull);
-            asm volatile("red.release.gpu.global.add.u64 [%0], %1;" :: "l"(G.gen), "l"(1ull) : "memory");
+            if (!G.is_root) asm volatile("red.release.gpu.global.add.u64 [%0], %1;" :: "l"(G.gen), "l"(1ull) : "memory");
         }
         ok = G.is_root ? (wait_flag_ge(G.arrived, G.arrive_target, G.timeout_ns, G.timed_out) ? 1 : 0) : -1;
     }
@@ -968,7 +997,7 @@ k_group_merge_big(const __grid_constant__ GroupStep G, int n) {
     if (threadIdx.x == 0) {
         __threadfence_system();
         last = atomicAdd(G.col_ticket, 1u) == gridDim.x - 1u;
-        if (last) { *G.col_ticket = 0u; __threadfence_system(); }
+        if (last) { *G.col_ticket = 0u; __threadfence_system(); epilogue_turn_done(G); }
     }
     __syncthreads();
     if (last && (int)threadIdx.x < G.npeers) red_release_sys_add(G.peer_clean[threadIdx.x], 1ull);
@@ -994,12 +1023,16 @@ k_group_push(const __grid_constant__ GroupStep G, int n, int op) {
     if (threadIdx.x == 0) {
         __threadfence_system();
         red_release_sys_add(G.arrived, 1ull);
-        asm volatile("red.release.gpu.global.add.u64 [%0], %1;" :: "l"(G.gen), "l"(1ull) : "memory");
+        if (!G.is_root) asm volatile("red.release.gpu.global.add.u64 [%0], %1;" :: "l"(G.gen), "l"(1ull) : "memory");
         state = G.is_root ? (wait_flag_ge(G.arrived, G.arrive_target, G.timeout_ns, G.timed_out) ? 2 : 3) : 0;
     }
     __syncthreads();
     if (state == 2) group_root_epilogue(G, n, threadIdx.x, blockDim.x, true);
     else if (state == 3 && (int)threadIdx.x < G.npeers) red_release_sys_add(G.peer_clean[threadIdx.x], 1ull);
+    if (state >= 2) {
+        __syncthreads();
+        if (threadIdx.x == 0) epilogue_turn_done(G);
+    }
 }
 
 // device-side barrier across the group: everybody release-adds the root's counter and spins on it (remote polling

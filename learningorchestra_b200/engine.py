@@ -74,6 +74,26 @@ class DeviceCounts:
             pass
 
 
+class DeviceColumn:
+    """Zero-copy view of one column slab for GPU consumers: implements ``__cuda_array_interface__`` (version 3), so
+    ``torch.as_tensor(col, device="cuda")``, ``cupy.asarray(col)`` or Numba see the slab in place.  Keeps its table
+    (and whatever the table keeps) alive."""
+
+    _TYPESTR = {N.LO_F64: "<f8", N.LO_F32: "<f4", N.LO_U8: "|u1"}
+
+    def __init__(self, table: "DeviceTable", col: int, keepalive=None):
+        if not 0 <= col < table.ncols:
+            raise IndexError(col)
+        self.table, self.col, self._keepalive = table, int(col), keepalive
+        self.data_ptr = table.base_ptr + self.col * table.pitch_bytes
+        self.nrows = table.nrows
+
+    @property
+    def __cuda_array_interface__(self):
+        return {"shape": (self.nrows,), "typestr": self._TYPESTR[self.table.dtype_code], "data": (self.data_ptr, False),
+                "version": 3, "strides": None}
+
+
 class DeviceTable:
     """Columnar table in HBM: ``ncols`` slabs of ``nrows`` elements of one dtype."""
 
@@ -99,6 +119,10 @@ class DeviceTable:
         N.check(self.engine._lib.lo_table_download_col(self.engine._ctx, self._h, col, row0,
                                                        out.ctypes.data_as(C.c_void_p), n, _stream_ptr(stream)))
         return out
+
+    def column_view(self, col: int, keepalive=None) -> DeviceColumn:
+        """The slab of one column as a ``__cuda_array_interface__`` object (no copy)."""
+        return DeviceColumn(self, col, keepalive)
 
     def fill_synthetic(self, kind: int, seed: int, row_offset: int = 0, lo: float = -1000.0, hi: float = 1000.0,
                        stream=None) -> "DeviceTable":

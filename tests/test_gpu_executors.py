@@ -406,3 +406,26 @@ def test_columnar_store_large_text_column_parse(engine):
     hist.wait(300)
     groups = db.find_one("big_h", {"_id": 1})["x"]
     assert sum(g["count"] for g in groups) == n + 1            # + the metadata document under null
+
+
+def test_builder_front_end_hands_the_frame_over_on_the_device(engine):
+    """the load -> filter -> drop-metadata-columns frame as zero-copy views of the resident slabs
+    (``__cuda_array_interface__``): a GPU consumer (torch here) reads them in place, no D2H."""
+    import torch
+    from learningorchestra_b200 import builder_frontend
+    db = utils.Database()
+    db.insert_one_in_file("d", {"_id": 0, "datasetName": "d", "finished": True, "fields": ["a", "b", "s"], "timeCreated": "t"})
+    rng = np.random.default_rng(2)
+    a = rng.normal(size=5000)
+    for i in range(5000):
+        db.insert_one_in_file("d", {"_id": i + 1, "a": float(a[i]), "b": (int(i) if i % 7 else None), "s": f"x{i}"})
+    with builder_frontend.device_frame(db, "d", engine) as frame:
+        assert frame.fields == ["a", "b"] and frame.nulls["b"] == len([i for i in range(5000) if i % 7 == 0])
+        ta = torch.as_tensor(frame.columns["a"][0], device="cuda")
+        tb = torch.as_tensor(frame.columns["b"][0], device="cuda")
+        assert ta.data_ptr() == frame.columns["a"][0].data_ptr          # in place
+        np.testing.assert_array_equal(ta.cpu().numpy(), a)
+        got_b = tb.cpu().numpy()
+        assert np.isnan(got_b[0]) and got_b[1] == 1.0 and int(np.isnan(got_b).sum()) == frame.nulls["b"]
+        host = builder_frontend.file_processor(db, "d", engine)          # the second form: pyarrow.Table on the host
+        assert host.column_names == ["a", "b", "s"] and host.num_rows == 5000
