@@ -230,36 +230,66 @@ __device__ __forceinline__ void bump4(uint8_t *priv, int b0, int b1, int b2, int
 // ---------------------------------------------------------------------------------------------
 // CTA-wide fold of the private byte histograms -> RED.64 into counts[]
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void zero_private(uint32_t *smem, int rows) {
-    for (int w = 0; w < rows; ++w) smem[w * kThreads + threadIdx.x] = 0u;
+// per-thread form (no barrier): each thread clears exactly the words it will count in
+__device__ __forceinline__ void zero_private_own(uint32_t *smem, int rows) {
+    for (int w = 0; w < rows; ++w) smem[w * kThreads + (threadIdx.x & (kThreads - 1))] = 0u;
 }
 
-// Each private byte is <= 255 and a row holds kThreads = 256 words: a lane sums 8 words into
-// packed 16-bit halves (<= 2040), the 32-lane butterfly keeps them <= 65280 — no overflow.
+// rows x kThreads words, 16 bytes per store; a thread zeroes OTHER threads' counters too, hence the barrier
+__device__ __forceinline__ void zero_private(uint32_t *smem, int rows) {
+    uint4 *p = reinterpret_cast<uint4 *>(smem);
+    const int n = rows * (kThreads / 4);
+    for (int i = threadIdx.x; i < n; i += kThreads) p[i] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
+}
+
+// Each private byte is <= 255 and a row holds kThreads = 256 words.  Warp `wp` owns rows wp, wp + 8, ..., wp + 56.
+// Per row a lane reads 8 words with two LDS.128 and sums them into two packed 16-bit pairs (even bytes / odd bytes,
+// <= 8 * 255 = 2040 each); the 16 packed registers of the warp's 8 rows are then reduced over the 32 lanes by a
+// TRANSPOSING butterfly — at every step a lane hands half of its registers to its partner and keeps the other half
+// (8 + 4 + 2 + 1 + 1 = 16 shuffles instead of 16 x 5; sums stay <= 65 280: no overflow) — and lane L ends up with
+// the total of register (L >> 1) & 15.  Then one RED.64 per non-empty bin into counts[].
 __device__ __forceinline__ void fold_and_flush(uint32_t *smem, int rows, int nbins,
                                                unsigned long long *counts /* this column's bins */) {
+    static_assert(kThreads / 32 == 8 && kHistRows == 64, "fold assumes 8 warps x 8 rows");
     uint32_t *folded = smem + kHistRows * kThreads;   // 256 words
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     __syncthreads();
-    for (int w = warp; w < rows; w += kThreads / 32) {
-        const uint32_t *row = smem + w * kThreads;
-        uint32_t even = 0, odd = 0;
+    uint32_t r[16];
 #pragma unroll
-        for (int i = 0; i < kThreads / 32; ++i) {
-            uint32_t x = row[lane + 32 * i];
-            even += x & 0x00FF00FFu;
-            odd  += (x >> 8) & 0x00FF00FFu;
-        }
+    for (int i = 0; i < 8; ++i) {
+        const int w = warp + 8 * i;
+        uint32_t even = 0u, odd = 0u;
+        if (w < rows) {                                  // warp-uniform
+            const uint4 a = *reinterpret_cast<const uint4 *>(smem + w * kThreads + 4 * lane);
+            const uint4 b = *reinterpret_cast<const uint4 *>(smem + w * kThreads + 128 + 4 * lane);
+            const uint32_t x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
-        for (int s = 16; s > 0; s >>= 1) {
-            even += __shfl_xor_sync(0xffffffffu, even, s);
-            odd  += __shfl_xor_sync(0xffffffffu, odd, s);
+            for (int q = 0; q < 8; ++q) {
+                even += x[q] & 0x00FF00FFu;
+                odd  += __byte_perm(x[q], 0u, 0x4341u);       // bytes 1 and 3 moved down: (x >> 8) & 0x00FF00FF in one op
+            }
         }
-        if (lane == 0) {
-            folded[4 * w + 0] = even & 0xFFFFu;
-            folded[4 * w + 1] = odd & 0xFFFFu;
-            folded[4 * w + 2] = even >> 16;
-            folded[4 * w + 3] = odd >> 16;
+        r[2 * i] = even;
+        r[2 * i + 1] = odd;
+    }
+#pragma unroll
+    for (int half = 8, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
+        const bool upper = (lane & bit) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const uint32_t send = upper ? r[i] : r[i + half];
+            const uint32_t keep = upper ? r[i + half] : r[i];
+            r[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+        }
+    }
+    const uint32_t total = r[0] + __shfl_xor_sync(0xffffffffu, r[0], 1);
+    if ((lane & 1) == 0) {
+        const int idx = (lane >> 1) & 15;                // which of the 16 registers this lane reduced
+        const int w = warp + 8 * (idx >> 1), parity = idx & 1;
+        if (w < rows) {
+            folded[4 * w + parity]     = total & 0xFFFFu;    // even reg: bins 4w, 4w+2 ; odd reg: bins 4w+1, 4w+3
+            folded[4 * w + 2 + parity] = total >> 16;
         }
     }
     __syncthreads();
@@ -456,7 +486,6 @@ k_project_cast_hist(const char *__restrict__ in_base, long long in_pitch,
         B.last = P.nbins - 1;
         rows = (P.nbins + 3) >> 2;
         zero_private(smem, rows);
-        // a thread only touches its own words until fold_and_flush: no barrier needed here
     }
 
     if (ALIGNED && n == kTileRows) {
@@ -628,7 +657,7 @@ k_project_cast_hist_tma(const char *__restrict__ in_base, long long in_pitch,
         B.r = __frcp_rn(B.w);
         B.last = P.nbins - 1;
         rows = (P.nbins + 3) >> 2;
-        zero_private(smem, rows);
+        zero_private_own(smem, rows);
     }
     __syncthreads();
 
@@ -847,7 +876,24 @@ k_hist_u8_cols(const uint8_t *__restrict__ in_base, long long in_pitch, long lon
     const U8Consts K = {P.p8, P.p11, P.p16, P.p19, P.p24, P.p27, P.p3};
     zero_private(smem, kHistRows);
 
-    if (ALIGNED) {
+    if (ALIGNED && n == kU8TileRows) {
+        // full tile: batch b+1's five 16-byte loads are in flight while batch b is being counted (register double
+        // buffer, as in the f64 kernel; without it every warp idles on its own loads between batches)
+        uint4 v[2][kU8Batch];
+        const uint8_t *src = in + (long long)threadIdx.x * kU8VecBytes;
+#pragma unroll
+        for (int u = 0; u < kU8Batch; ++u) v[0][u] = ldg128_stream(src + (long long)u * kThreads * kU8VecBytes);
+#pragma unroll
+        for (int b = 0; b < kU8Batches; ++b) {
+            if (b + 1 < kU8Batches) {
+#pragma unroll
+                for (int u = 0; u < kU8Batch; ++u)
+                    v[(b + 1) & 1][u] = ldg128_stream(src + (long long)((b + 1) * kU8Batch + u) * kThreads * kU8VecBytes);
+            }
+#pragma unroll
+            for (int u = 0; u < kU8Batch; ++u) bump_vec16<MODE>(priv, v[b & 1][u], K);
+        }
+    } else if (ALIGNED) {
 #pragma unroll 1
         for (int b = 0; b < kU8Batches; ++b) {
             const long long e0 = ((long long)b * kU8Batch * kThreads + threadIdx.x) * kU8VecBytes;
