@@ -178,6 +178,7 @@ int configure_kernels() {
     LO_TRY(allow_smem(lo::k_hist_u8_cols<true, 4>));
     LO_TRY(allow_smem(lo::k_hist_u8_cols<true, 5>));
     LO_TRY(allow_smem(lo::k_hist_u8_cols<true, 6>));
+    LO_TRY(allow_smem(lo::k_hist_u8_cols<true, 7>));
     LO_TRY(allow_smem(lo::k_hist_u8_cols<false, 4>));
     return LO_OK;
 }
@@ -339,6 +340,7 @@ int hist_u8_impl(lo_ctx *ctx, const lo_table *in, const int32_t *col_idx, int32_
         else if (mode == 2) LO_U8_LAUNCH(true, 2);
         else if (mode == 5) LO_U8_LAUNCH(true, 5);
         else if (mode == 6) LO_U8_LAUNCH(true, 6);
+        else if (mode == 7) LO_U8_LAUNCH(true, 7);
         else                LO_U8_LAUNCH(true, 4);
 #undef LO_U8_LAUNCH
         LO_CUDA(cudaGetLastError());
