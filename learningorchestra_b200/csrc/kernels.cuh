@@ -485,7 +485,6 @@ k_project_cast_hist(const char *__restrict__ in_base, long long in_pitch,
         B.r = __frcp_rn(B.w);
         B.last = P.nbins - 1;
         rows = (P.nbins + 3) >> 2;
-        zero_private(smem, rows);
     }
 
     if (ALIGNED && n == kTileRows) {
@@ -498,6 +497,7 @@ k_project_cast_hist(const char *__restrict__ in_base, long long in_pitch,
 #pragma unroll
             for (int u = 0; u < kPfBatch; ++u)
                 ldg256_stream(src + (long long)(pb * kPfBatch + u) * kThreads * kVec, v[pb][u]);
+        if (HIST) zero_private(smem, rows);        // the first batch's DRAM latency overlaps the clearing and its barrier
 #pragma unroll 1
         for (int b0 = 0; b0 < kPfBatches; b0 += kPfBuf) {
 #pragma unroll
@@ -523,6 +523,7 @@ k_project_cast_hist(const char *__restrict__ in_base, long long in_pitch,
             }
         }
     } else if (ALIGNED) {
+        if (HIST) zero_private(smem, rows);
 #pragma unroll 1
         for (int b = 0; b < kBatches; ++b) {
             const long long e0 = ((long long)b * kBatch * kThreads + threadIdx.x) * kVec;   // first element of vector 0
@@ -563,6 +564,7 @@ k_project_cast_hist(const char *__restrict__ in_base, long long in_pitch,
         }
     } else {
         // unaligned slabs (wrapped foreign memory): scalar, lane-contiguous accesses
+        if (HIST) zero_private(smem, rows);
 #pragma unroll 1
         for (int i = 0; i < kElemsPerThread; ++i) {
             const long long e = (long long)i * kThreads + threadIdx.x;
@@ -926,15 +928,15 @@ k_hist_u8_cols(const uint8_t *__restrict__ in_base, long long in_pitch, long lon
         K.p3 = 4u * threadIdx.x;
         K.p8 = ((4u * threadIdx.x) >> 8) * 0x01010101u;
     }
-    zero_private(smem, kHistRows);
-
     if (ALIGNED && n == kU8TileRows) {
         // full tile: batch b+1's five 16-byte loads are in flight while batch b is being counted (register double
-        // buffer, as in the f64 kernel; without it every warp idles on its own loads between batches)
+        // buffer, as in the f64 kernel; without it every warp idles on its own loads between batches).  The first
+        // batch is requested BEFORE the counters are cleared, so its DRAM latency overlaps the clearing and its barrier.
         uint4 v[2][kU8Batch];
         const uint8_t *src = in + (long long)threadIdx.x * kU8VecBytes;
 #pragma unroll
         for (int u = 0; u < kU8Batch; ++u) v[0][u] = ldg128_stream(src + (long long)u * kThreads * kU8VecBytes);
+        zero_private(smem, kHistRows);
 #pragma unroll
         for (int b = 0; b < kU8Batches; ++b) {
             if (b + 1 < kU8Batches) {
@@ -950,6 +952,7 @@ k_hist_u8_cols(const uint8_t *__restrict__ in_base, long long in_pitch, long lon
             }
         }
     } else if (ALIGNED) {
+        zero_private(smem, kHistRows);
 #pragma unroll 1
         for (int b = 0; b < kU8Batches; ++b) {
             const long long e0 = ((long long)b * kU8Batch * kThreads + threadIdx.x) * kU8VecBytes;
@@ -971,6 +974,7 @@ k_hist_u8_cols(const uint8_t *__restrict__ in_base, long long in_pitch, long lon
             }
         }
     } else {
+        zero_private(smem, kHistRows);
 #pragma unroll 1
         for (int i = 0; i < kU8ElemsPerThread; ++i) {
             const long long e = (long long)i * kThreads + threadIdx.x;
