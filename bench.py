@@ -92,19 +92,58 @@ def workload_text(workload: str, rows: int, ncols: int, k: int) -> str:
 
 
 class ClockSampler:
-    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md 'clocks line').  The process is started
-    before the warm-up (nvidia-smi needs ~100 ms to come up); every line is stamped on receipt and only the
-    samples that fall inside [mark_start, mark_end] are summarised."""
+    """SM clock / power / throttle reasons sampled DURING the timed region (B200_PROFILING.md 'clocks line').
+    NVML is polled from a thread every ~2 ms (the timed region of an 8-GPU run lasts ~15 ms: `nvidia-smi -lms` cannot
+    go below 100 ms and would see it once at best); `nvidia-smi -lms 100` is the fallback when NVML is not importable.
+    Every sample is stamped on receipt and only those inside [mark_start, mark_end] are summarised."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, device: int):
         self.device, self.rows, self.proc, self.thread = device, [], None, None
         self.t0 = self.t1 = None
+        self.source, self._stop, self._smax = None, threading.Event(), None
+
+    def _physical_index(self) -> int:
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[self.device])
+            except Exception:
+                pass
+        return self.device
 
     def start(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self._smax = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            masks = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                     "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                     "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                     "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+            reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+
+            def poll():
+                while not self._stop.is_set():
+                    try:
+                        sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                        pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                        bits = int(reasons_fn(h))
+                        self.rows.append((time.time(), sm, pw, [n for n in self.NAMES if bits & masks[n]]))
+                    except Exception:
+                        pass
+                    time.sleep(0.002)
+            self.source = "nvml, 2 ms poll"
+            self.thread = threading.Thread(target=poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.source = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-i", str(self.device), "-lms", "100"], stdout=subprocess.PIPE,
@@ -112,19 +151,26 @@ class ClockSampler:
         except Exception:
             self.proc = None
             return
+        self.source = "nvidia-smi -lms 100"
         self.thread = threading.Thread(target=self._pump, daemon=True)
         self.thread.start()
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+            r = [c.strip() for c in line.split(",")]
+            try:
+                self._smax = float(r[2])
+                self.rows.append((time.time(), float(r[1]), float(r[3]),
+                                  [n for n, v in zip(self.NAMES, r[5:9]) if v.lower().startswith("active")]))
+            except Exception:
+                continue
 
     def wait_ready(self, wait_s: float = 2.0):
-        """Block until nvidia-smi is actually producing lines.  Must be called BEFORE the barrier that precedes
-        the timed region: only rank 0 samples, and waiting after the barrier would let the other ranks start
-        their timed steps and then sit in the merge waiting for rank 0."""
+        """Block until samples are actually arriving.  Must be called BEFORE the barrier that precedes the timed
+        region: only rank 0 samples, and waiting after the barrier would let the other ranks start their timed steps
+        and then sit in the merge waiting for rank 0."""
         deadline = time.time() + wait_s
-        while self.proc is not None and not self.rows and time.time() < deadline:
+        while self.source is not None and not self.rows and time.time() < deadline:
             time.sleep(0.01)
 
     def mark_start(self):
@@ -134,29 +180,23 @@ class ClockSampler:
         self.t1 = time.time()
 
     def stop(self) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.12)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        inside = [r for t, r in self.rows if self.t0 is not None and self.t0 <= t <= (self.t1 or t) + 0.1]
-        used = inside if inside else [r for _t, r in self.rows[-3:]]
-        sm, smax, power, reasons = [], [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in used:
+        if self.source is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML and no nvidia-smi"]}
+        time.sleep(0.01 if self.proc is None else 0.12)
+        self._stop.set()
+        if self.proc is not None:
+            self.proc.terminate()
             try:
-                sm.append(float(r[1])); smax.append(float(r[2])); power.append(float(r[3]))
+                self.proc.wait(timeout=2)
             except Exception:
-                continue
-            for nm, v in zip(names, r[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm),
-                "samples_inside_timed_region": len(inside), "reasons": sorted(reasons)}
+                self.proc.kill()
+        inside = [r for r in self.rows if self.t0 is not None and self.t0 <= r[0] <= (self.t1 or r[0])]
+        used = inside if inside else self.rows[-3:]
+        sm = [r[1] for r in used]
+        reasons = sorted({n for r in used for n in r[3]})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_min_mhz": min(sm) if sm else None,
+                "sm_max_mhz": self._smax, "power_w_max": max((r[2] for r in used), default=None), "samples": len(used),
+                "samples_inside_timed_region": len(inside), "reasons": reasons, "source": self.source}
 
 
 # ======================================================================================================
@@ -217,6 +257,24 @@ def cpu_pass_setup(workload: str, sample_rows: int, ncols: int):
     return one_pass, threads, (ins, outs)
 
 
+def _host_info() -> dict:
+    """What the CPU arm actually had: the pool's 1-GPU boxes are slices of a host (same 128 logical CPUs visible, a
+    fraction of the machine behind them), the 8-GPU box is the whole machine — the arm's rows/s differs ~6x between
+    them for that reason, not because of the code (VERDICT r1 weak #5)."""
+    info = {"logical_cpus": os.cpu_count(), "affinity_cpus": len(os.sched_getaffinity(0))}
+    for key, path in (("cgroup_cpu_max", "/sys/fs/cgroup/cpu.max"), ("loadavg", "/proc/loadavg")):
+        try:
+            info[key] = Path(path).read_text().strip()
+        except Exception:
+            pass
+    try:
+        import psutil
+        info["ram_gb"] = round(psutil.virtual_memory().total / 2 ** 30)
+    except Exception:
+        pass
+    return info
+
+
 def _sample_text(workload, sample_rows, rows, ncols, threads):
     whole = "the whole table" if sample_rows == rows else f"the first {sample_rows} rows of the {rows}-row table"
     return (f"{whole} x {ncols} cols of the same synthetic data, host-resident columns generated and scanned by the "
@@ -236,7 +294,7 @@ def run_cpu_baseline(workload: str, rows: int, ncols: int, requested_rows: int, 
         times.append(time.perf_counter() - t0)
     med = statistics.median(times)
     return {"value": sample_rows / med, "unit": "rows/s", "cores": threads, "kind": "port", "passes": len(times),
-            "sample_rows": sample_rows, "same_config": sample_rows == rows,
+            "sample_rows": sample_rows, "same_config": sample_rows == rows, "host": _host_info(),
             "sample": _sample_text(workload, sample_rows, rows, ncols, threads) + f"; median of {len(times)} passes"}
 
 
@@ -268,7 +326,7 @@ def run_reference_arm(args) -> None:
                    "nbins": NBINS if w != "s10" else 0, "sample_rows": sample_rows, "threads": threads,
                    "same_config": sample_rows == rows,
                    "note": "reference PySpark/MongoDB stack is not runnable offline; this is the CPU oracle port"},
-        "cpu_baseline": {"value": value, "unit": "rows/s", "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "rows/s", "cores": threads, "kind": "port", "sample": sample, "host": _host_info()},
         "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }), flush=True)
@@ -557,7 +615,7 @@ def run_gpu(args) -> int:
         # is skipped on ALL ranks together rather than leaving some of them waiting in a collective
         setup_error = None
         try:
-            hin = eng.pinned_empty((k, e2e_rows), np.uint8 if w == "m" else np.float64)
+            hin = eng.pinned_empty((k, e2e_rows), np.uint8 if w == "m" else np.float64, write_combined=args.e2e_wc)
             hout = eng.pinned_empty((k, e2e_rows), np.float32) if w != "m" else None
             for j in range(k):   # host inputs = the projected columns of this rank's shard (device -> pinned host, untimed)
                 table.shards[0].to_numpy(cols[j], 0, e2e_rows, out=hin[j])
@@ -697,6 +755,7 @@ def main():
     ap.add_argument("--e2e-rows", type=int, default=0, help="cap on e2e rows per rank (0 = whole shard if RAM allows)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-wc", action="store_true", help="e2e input buffers in write-combined pinned memory (A/B knob)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--executor-rows", type=int, default=10_000_000,
                     help="rows of the in-process collection for the executor-level numbers (s100 at N = 1; 0 = skip)")

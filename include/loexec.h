@@ -106,6 +106,10 @@ int         lo_launch_count(const lo_ctx *ctx, int64_t *out);
 
 /* ---- pinned host memory (so *_host calls can overlap copies with kernels) ------------ */
 int lo_host_alloc(lo_ctx *ctx, size_t bytes, void **out);
+/* flags: LO_HOST_WRITE_COMBINED — for buffers the host only WRITES (staging inputs for the GPU): uncached on the CPU
+ * side, no snooping on the PCIe read; CPU reads from such memory are very slow */
+#define LO_HOST_WRITE_COMBINED 1
+int lo_host_alloc_flags(lo_ctx *ctx, size_t bytes, int32_t flags, void **out);
 int lo_host_free(lo_ctx *ctx, void *p);
 
 /* ---- tables --------------------------------------------------------------------------- */

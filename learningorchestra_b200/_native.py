@@ -74,6 +74,7 @@ SIGNATURES = {
     "lo_set_tma": (C.c_int, [_P, C.c_int]),
     "lo_launch_count": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "lo_host_alloc": (C.c_int, [_P, C.c_size_t, C.POINTER(_P)]),
+    "lo_host_alloc_flags": (C.c_int, [_P, C.c_size_t, C.c_int32, C.POINTER(_P)]),
     "lo_host_free": (C.c_int, [_P, _P]),
     "lo_table_alloc": (C.c_int, [_P, C.c_int, C.c_int64, C.c_int32, C.POINTER(_P)]),
     "lo_table_wrap": (C.c_int, [_P, C.c_int, C.c_int64, C.c_int32, _P, C.c_int64, C.POINTER(_P)]),

@@ -512,6 +512,16 @@ int lo_host_alloc(lo_ctx *ctx, size_t bytes, void **out) {
     return LO_OK;
 }
 
+int lo_host_alloc_flags(lo_ctx *ctx, size_t bytes, int32_t flags, void **out) {
+    LO_TRY(check_ctx(ctx));
+    if (!out) return fail(LO_ERR_INVALID, "out is NULL");
+    if (flags & ~LO_HOST_WRITE_COMBINED) return fail(LO_ERR_INVALID, "unknown flags 0x%x", flags);
+    *out = nullptr;
+    if (bytes == 0) return LO_OK;
+    LO_CUDA(cudaHostAlloc(out, bytes, cudaHostAllocPortable | ((flags & LO_HOST_WRITE_COMBINED) ? cudaHostAllocWriteCombined : 0)));
+    return LO_OK;
+}
+
 int lo_host_free(lo_ctx *ctx, void *p) {
     LO_TRY(check_ctx(ctx));
     if (p) LO_CUDA(cudaFreeHost(p));

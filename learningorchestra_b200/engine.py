@@ -217,12 +217,13 @@ class Engine:
     def wrap_counts(self, k: int, nbins: int, ptr: int, keepalive=None) -> DeviceCounts:
         return DeviceCounts(self, k, nbins, ptr=ptr, keepalive=keepalive)
 
-    def pinned_empty(self, shape, dtype) -> np.ndarray:
-        """numpy array backed by page-locked host memory (freed by close())."""
+    def pinned_empty(self, shape, dtype, write_combined: bool = False) -> np.ndarray:
+        """numpy array backed by page-locked host memory (freed by close()).  ``write_combined``: for staging buffers
+        the host only writes (GPU inputs) — never read them back on the CPU."""
         dtype = np.dtype(dtype)
         nbytes = int(np.prod(shape)) * dtype.itemsize
         p = C.c_void_p()
-        N.check(self._lib.lo_host_alloc(self._ctx, max(nbytes, 1), C.byref(p)))
+        N.check(self._lib.lo_host_alloc_flags(self._ctx, max(nbytes, 1), 1 if write_combined else 0, C.byref(p)))
         self._pinned[p.value] = p
         buf = (C.c_char * max(nbytes, 1)).from_address(p.value)
         return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)

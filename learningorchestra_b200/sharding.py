@@ -390,8 +390,8 @@ class ShardedEngine:
     def minmax_cast_host(self, cols):
         return self.engines[0].minmax_cast_host(cols)
 
-    def pinned_empty(self, shape, dtype):
-        return self.engines[0].pinned_empty(shape, dtype)
+    def pinned_empty(self, shape, dtype, write_combined: bool = False):
+        return self.engines[0].pinned_empty(shape, dtype, write_combined)
 
     def parse_number_host(self, cells):
         return self.engines[0].parse_number_host(cells)
