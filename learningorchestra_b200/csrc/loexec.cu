@@ -7,6 +7,7 @@
 #include "kernels.cuh"
 
 #include <atomic>
+#include <condition_variable>
 #include <cctype>
 #include <chrono>
 #include <cmath>
@@ -73,23 +74,32 @@ struct lo_table {
 };
 
 constexpr int kSlots = 3;      // staging slots of the *_host pipeline: H2D of chunk c+1/c+2 overlaps kernel c and D2H c-1
+constexpr int kMaxStageSets = 4;
+
+struct StageSet {
+    cudaStream_t compute = nullptr, h2d = nullptr, d2h = nullptr;
+    char        *in[kSlots]  = {nullptr, nullptr, nullptr};
+    char        *out[kSlots] = {nullptr, nullptr, nullptr};
+    size_t       in_bytes = 0, out_bytes = 0;
+    unsigned long long *counts = nullptr;
+    size_t       counts_n = 0;
+    cudaEvent_t  ev_h2d[kSlots] = {}, ev_k[kSlots] = {}, ev_d2h[kSlots] = {};
+};
 
 struct lo_ctx {
     int          device;
     int          sm_count;
     size_t       hbm_bytes;
     cudaStream_t stream;       // default stream for NULL `stream` arguments
-    cudaStream_t h2d, d2h;     // copy streams of the *_host pipeline
     std::atomic<int64_t> launches{0};
     std::atomic<bool> use_tma{false};   // LOEXEC_TMA=1 or lo_set_tma(): stage slabs through smem with cp.async.bulk
-    // *_host pipeline staging (one pipeline at a time per context)
-    std::mutex   host_mu;
-    char        *stage_in[kSlots]  = {nullptr, nullptr, nullptr};
-    char        *stage_out[kSlots] = {nullptr, nullptr, nullptr};
-    size_t       stage_in_bytes = 0, stage_out_bytes = 0;
-    unsigned long long *host_counts_dev = nullptr;
-    size_t       host_counts_n = 0;
-    cudaEvent_t  ev_h2d[kSlots], ev_k[kSlots], ev_d2h[kSlots];
+    // *_host pipelines: each call borrows a StageSet (its own three streams, staging slots, events, count scratch)
+    // from this pool, so concurrent calls on one context — the REST services run a thread per job — overlap instead
+    // of queueing; at most kMaxStageSets exist, further callers wait for one to come back
+    std::mutex   pool_mu;
+    std::condition_variable pool_cv;
+    std::vector<StageSet *> free_sets;
+    int          nsets = 0;
 };
 
 namespace {
@@ -349,34 +359,94 @@ int hist_u8_impl(lo_ctx *ctx, const lo_table *in, const int32_t *col_idx, int32_
     return LO_OK;
 }
 
-int ensure_stage(lo_ctx *ctx, size_t in_bytes, size_t out_bytes, size_t ncounts) {
-    if (in_bytes > ctx->stage_in_bytes) {
+int ensure_stage(StageSet *st, size_t in_bytes, size_t out_bytes, size_t ncounts) {
+    if (in_bytes > st->in_bytes) {
         for (int i = 0; i < kSlots; ++i) {
-            if (ctx->stage_in[i]) cudaFree(ctx->stage_in[i]);
-            ctx->stage_in[i] = nullptr;
+            if (st->in[i]) cudaFree(st->in[i]);
+            st->in[i] = nullptr;
         }
-        ctx->stage_in_bytes = 0;
-        for (int i = 0; i < kSlots; ++i) LO_CUDA(cudaMalloc((void **)&ctx->stage_in[i], in_bytes));
-        ctx->stage_in_bytes = in_bytes;
+        st->in_bytes = 0;
+        for (int i = 0; i < kSlots; ++i) LO_CUDA(cudaMalloc((void **)&st->in[i], in_bytes));
+        st->in_bytes = in_bytes;
     }
-    if (out_bytes > ctx->stage_out_bytes) {
+    if (out_bytes > st->out_bytes) {
         for (int i = 0; i < kSlots; ++i) {
-            if (ctx->stage_out[i]) cudaFree(ctx->stage_out[i]);
-            ctx->stage_out[i] = nullptr;
+            if (st->out[i]) cudaFree(st->out[i]);
+            st->out[i] = nullptr;
         }
-        ctx->stage_out_bytes = 0;
-        for (int i = 0; i < kSlots; ++i) LO_CUDA(cudaMalloc((void **)&ctx->stage_out[i], out_bytes));
-        ctx->stage_out_bytes = out_bytes;
+        st->out_bytes = 0;
+        for (int i = 0; i < kSlots; ++i) LO_CUDA(cudaMalloc((void **)&st->out[i], out_bytes));
+        st->out_bytes = out_bytes;
     }
-    if (ncounts > ctx->host_counts_n) {
-        if (ctx->host_counts_dev) cudaFree(ctx->host_counts_dev);
-        ctx->host_counts_dev = nullptr;
-        ctx->host_counts_n = 0;
-        LO_CUDA(cudaMalloc((void **)&ctx->host_counts_dev, ncounts * sizeof(unsigned long long)));
-        ctx->host_counts_n = ncounts;
+    if (ncounts > st->counts_n) {
+        if (st->counts) cudaFree(st->counts);
+        st->counts = nullptr;
+        st->counts_n = 0;
+        LO_CUDA(cudaMalloc((void **)&st->counts, ncounts * sizeof(unsigned long long)));
+        st->counts_n = ncounts;
     }
     return LO_OK;
 }
+
+void stage_set_destroy(StageSet *st) {
+    if (!st) return;
+    for (int i = 0; i < kSlots; ++i) {
+        if (st->in[i]) cudaFree(st->in[i]);
+        if (st->out[i]) cudaFree(st->out[i]);
+        if (st->ev_h2d[i]) cudaEventDestroy(st->ev_h2d[i]);
+        if (st->ev_k[i]) cudaEventDestroy(st->ev_k[i]);
+        if (st->ev_d2h[i]) cudaEventDestroy(st->ev_d2h[i]);
+    }
+    if (st->counts) cudaFree(st->counts);
+    if (st->compute) cudaStreamDestroy(st->compute);
+    if (st->h2d) cudaStreamDestroy(st->h2d);
+    if (st->d2h) cudaStreamDestroy(st->d2h);
+    delete st;
+}
+
+int stage_set_create(StageSet **out) {
+    StageSet *st = new (std::nothrow) StageSet;
+    if (!st) return fail(LO_ERR_NOMEM, "out of host memory");
+    auto setup = [&]() -> int {
+        LO_CUDA(cudaStreamCreateWithFlags(&st->compute, cudaStreamNonBlocking));
+        LO_CUDA(cudaStreamCreateWithFlags(&st->h2d, cudaStreamNonBlocking));
+        LO_CUDA(cudaStreamCreateWithFlags(&st->d2h, cudaStreamNonBlocking));
+        for (int i = 0; i < kSlots; ++i) {
+            LO_CUDA(cudaEventCreateWithFlags(&st->ev_h2d[i], cudaEventDisableTiming));
+            LO_CUDA(cudaEventCreateWithFlags(&st->ev_k[i], cudaEventDisableTiming));
+            LO_CUDA(cudaEventCreateWithFlags(&st->ev_d2h[i], cudaEventDisableTiming));
+        }
+        return LO_OK;
+    };
+    const int rc = setup();
+    if (rc != LO_OK) { const std::string msg = g_err; stage_set_destroy(st); g_err = msg; return rc; }
+    *out = st;
+    return LO_OK;
+}
+
+// borrow a stage set for the duration of one *_host call
+struct StageLease {
+    lo_ctx *ctx;
+    StageSet *st = nullptr;
+    explicit StageLease(lo_ctx *c) : ctx(c) {}
+    int acquire() {
+        std::unique_lock<std::mutex> lk(ctx->pool_mu);
+        for (;;) {
+            if (!ctx->free_sets.empty()) { st = ctx->free_sets.back(); ctx->free_sets.pop_back(); return LO_OK; }
+            if (ctx->nsets < kMaxStageSets) { ctx->nsets += 1; break; }
+            ctx->pool_cv.wait(lk);
+        }
+        lk.unlock();
+        const int rc = stage_set_create(&st);
+        if (rc != LO_OK) { std::lock_guard<std::mutex> g(ctx->pool_mu); ctx->nsets -= 1; ctx->pool_cv.notify_one(); }
+        return rc;
+    }
+    ~StageLease() {
+        if (!st) return;
+        { std::lock_guard<std::mutex> g(ctx->pool_mu); ctx->free_sets.push_back(st); }
+        ctx->pool_cv.notify_one();
+    }
+};
 
 // rows per chunk of the *_host pipeline: ~LOEXEC_CHUNK_MB (default 512) MiB of input per chunk, whole tiles
 int64_t chunk_rows_for(int64_t nrows, int32_t k, size_t elem_bytes, int64_t tile_rows) {
@@ -433,17 +503,9 @@ int lo_init(int device, lo_ctx **out) {
     ctx->device    = device;
     ctx->sm_count  = prop.multiProcessorCount;
     ctx->hbm_bytes = prop.totalGlobalMem;
-    ctx->stream = ctx->h2d = ctx->d2h = nullptr;
-    for (int i = 0; i < kSlots; ++i) ctx->ev_h2d[i] = ctx->ev_k[i] = ctx->ev_d2h[i] = nullptr;
+    ctx->stream = nullptr;
     auto setup = [&]() -> int {
         LO_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-        LO_CUDA(cudaStreamCreateWithFlags(&ctx->h2d, cudaStreamNonBlocking));
-        LO_CUDA(cudaStreamCreateWithFlags(&ctx->d2h, cudaStreamNonBlocking));
-        for (int i = 0; i < kSlots; ++i) {
-            LO_CUDA(cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming));
-            LO_CUDA(cudaEventCreateWithFlags(&ctx->ev_k[i], cudaEventDisableTiming));
-            LO_CUDA(cudaEventCreateWithFlags(&ctx->ev_d2h[i], cudaEventDisableTiming));
-        }
         return configure_kernels();
     };
     if (const char *e = getenv("LOEXEC_TMA")) ctx->use_tma.store(e[0] == '1');
@@ -462,17 +524,9 @@ int lo_shutdown(lo_ctx *ctx) {
     if (!ctx) return LO_OK;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    for (int i = 0; i < kSlots; ++i) {
-        if (ctx->stage_in[i]) cudaFree(ctx->stage_in[i]);
-        if (ctx->stage_out[i]) cudaFree(ctx->stage_out[i]);
-        if (ctx->ev_h2d[i]) cudaEventDestroy(ctx->ev_h2d[i]);
-        if (ctx->ev_k[i]) cudaEventDestroy(ctx->ev_k[i]);
-        if (ctx->ev_d2h[i]) cudaEventDestroy(ctx->ev_d2h[i]);
-    }
-    if (ctx->host_counts_dev) cudaFree(ctx->host_counts_dev);
+    for (StageSet *st : ctx->free_sets) stage_set_destroy(st);
+    ctx->free_sets.clear();
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
-    if (ctx->h2d) cudaStreamDestroy(ctx->h2d);
-    if (ctx->d2h) cudaStreamDestroy(ctx->d2h);
     delete ctx;
     return LO_OK;
 }
@@ -815,53 +869,55 @@ int host_pipeline(lo_ctx *ctx, const void *const *in_cols, int in_dtype, int64_t
     double h2d = 0, d2h = 0;
     if (counts_host && ncounts && !counts_target) memset(counts_host, 0, ncounts * 8);
     if (nrows > 0) {
-        std::lock_guard<std::mutex> lk(ctx->host_mu);
+        StageLease lease(ctx);
+        LO_TRY(lease.acquire());
+        StageSet *st = lease.st;
         auto body = [&]() -> int {
             const int64_t crows = chunk_rows_for(nrows, k, ies, tile_rows);
             const int64_t in_pitch  = (int64_t)(((size_t)crows * ies + 255) / 256 * 256);
             const int64_t out_pitch = (int64_t)(((size_t)crows * oes + 255) / 256 * 256);
-            LO_TRY(ensure_stage(ctx, (size_t)in_pitch * k, out_cols ? (size_t)out_pitch * k : 0, counts_target ? 0 : ncounts));
-            unsigned long long *cdev = counts_target ? counts_target : ctx->host_counts_dev;
-            if (ncounts && !counts_target) LO_CUDA(cudaMemsetAsync(cdev, 0, ncounts * 8, ctx->stream));
+            LO_TRY(ensure_stage(st, (size_t)in_pitch * k, out_cols ? (size_t)out_pitch * k : 0, counts_target ? 0 : ncounts));
+            unsigned long long *cdev = counts_target ? counts_target : st->counts;
+            if (ncounts && !counts_target) LO_CUDA(cudaMemsetAsync(cdev, 0, ncounts * 8, st->compute));
             const int64_t nchunks = (nrows + crows - 1) / crows;
             for (int64_t c = 0; c < nchunks; ++c) {
                 const int slot = (int)(c % kSlots);
                 const int64_t r0 = c * crows, n = std::min(crows, nrows - r0);
-                if (c >= kSlots) LO_CUDA(cudaStreamWaitEvent(ctx->h2d, ctx->ev_k[slot], 0));
+                if (c >= kSlots) LO_CUDA(cudaStreamWaitEvent(st->h2d, st->ev_k[slot], 0));
                 for (int j = 0; j < k; ++j)
-                    LO_CUDA(cudaMemcpyAsync(ctx->stage_in[slot] + (int64_t)j * in_pitch,
+                    LO_CUDA(cudaMemcpyAsync(st->in[slot] + (int64_t)j * in_pitch,
                                             (const char *)in_cols[j] + r0 * (int64_t)ies, (size_t)n * ies,
-                                            cudaMemcpyHostToDevice, ctx->h2d));
+                                            cudaMemcpyHostToDevice, st->h2d));
                 h2d += (double)n * ies * k;
-                LO_CUDA(cudaEventRecord(ctx->ev_h2d[slot], ctx->h2d));
-                LO_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[slot], 0));
-                if (c >= kSlots && out_cols) LO_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[slot], 0));
-                lo_table tin  = {in_dtype, n, k, in_pitch, ctx->stage_in[slot], false, ctx->device};
-                lo_table tout = {out_dtype, n, k, out_pitch, out_cols ? ctx->stage_out[slot] : nullptr, false, ctx->device};
-                LO_TRY(launch(&tin, out_cols ? &tout : nullptr, cdev));
-                LO_CUDA(cudaEventRecord(ctx->ev_k[slot], ctx->stream));
+                LO_CUDA(cudaEventRecord(st->ev_h2d[slot], st->h2d));
+                LO_CUDA(cudaStreamWaitEvent(st->compute, st->ev_h2d[slot], 0));
+                if (c >= kSlots && out_cols) LO_CUDA(cudaStreamWaitEvent(st->compute, st->ev_d2h[slot], 0));
+                lo_table tin  = {in_dtype, n, k, in_pitch, st->in[slot], false, ctx->device};
+                lo_table tout = {out_dtype, n, k, out_pitch, out_cols ? st->out[slot] : nullptr, false, ctx->device};
+                LO_TRY(launch(&tin, out_cols ? &tout : nullptr, cdev, st->compute));
+                LO_CUDA(cudaEventRecord(st->ev_k[slot], st->compute));
                 if (out_cols) {
-                    LO_CUDA(cudaStreamWaitEvent(ctx->d2h, ctx->ev_k[slot], 0));
+                    LO_CUDA(cudaStreamWaitEvent(st->d2h, st->ev_k[slot], 0));
                     for (int j = 0; j < k; ++j)
                         LO_CUDA(cudaMemcpyAsync((char *)out_cols[j] + r0 * (int64_t)oes,
-                                                ctx->stage_out[slot] + (int64_t)j * out_pitch, (size_t)n * oes,
-                                                cudaMemcpyDeviceToHost, ctx->d2h));
+                                                st->out[slot] + (int64_t)j * out_pitch, (size_t)n * oes,
+                                                cudaMemcpyDeviceToHost, st->d2h));
                     d2h += (double)n * oes * k;
-                    LO_CUDA(cudaEventRecord(ctx->ev_d2h[slot], ctx->d2h));
+                    LO_CUDA(cudaEventRecord(st->ev_d2h[slot], st->d2h));
                 }
             }
             if (ncounts && counts_host && !counts_target) {
-                LO_CUDA(cudaMemcpyAsync(counts_host, cdev, ncounts * 8, cudaMemcpyDeviceToHost, ctx->stream));
+                LO_CUDA(cudaMemcpyAsync(counts_host, cdev, ncounts * 8, cudaMemcpyDeviceToHost, st->compute));
                 d2h += (double)ncounts * 8;
             }
             return LO_OK;
         };
         const int rc = body();
         // success or failure: nothing may still be reading the caller's buffers or the staging slots when the
-        // lock is released (on failure the message of the FIRST error is kept)
+        // stage set goes back to the pool (on failure the message of the FIRST error is kept)
         const std::string first = g_err;
-        const cudaError_t e1 = cudaStreamSynchronize(ctx->stream), e2 = cudaStreamSynchronize(ctx->d2h),
-                          e3 = cudaStreamSynchronize(ctx->h2d);
+        const cudaError_t e1 = cudaStreamSynchronize(st->compute), e2 = cudaStreamSynchronize(st->d2h),
+                          e3 = cudaStreamSynchronize(st->h2d);
         if (rc != LO_OK) { g_err = first; return rc; }
         if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
             return fail(LO_ERR_CUDA, "host pipeline: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2 != cudaSuccess ? e2 : e3));
@@ -903,8 +959,8 @@ int lo_project_cast_hist_host(lo_ctx *ctx, const double *const *in_cols, int64_t
     const size_t ncounts = spec ? (size_t)k * (size_t)spec->nbins : 0;
     return host_pipeline(ctx, (const void *const *)in_cols, LO_F64, nrows, k, (void *const *)out_cols, LO_F32,
                          lo::kTileRows, ncounts, counts, timing,
-                         [&](lo_table *tin, lo_table *tout, unsigned long long *cdev) {
-                             return project_cast_hist_impl(ctx, tin, ident.data(), k, tout, spec, (uint64_t *)cdev, ctx->stream);
+                         [&](lo_table *tin, lo_table *tout, unsigned long long *cdev, cudaStream_t cs) {
+                             return project_cast_hist_impl(ctx, tin, ident.data(), k, tout, spec, (uint64_t *)cdev, cs);
                          });
 }
 
@@ -916,8 +972,8 @@ int lo_hist_u8_cols_host(lo_ctx *ctx, const uint8_t *const *in_cols, int64_t nro
     std::vector<int32_t> ident(k);
     for (int j = 0; j < k; ++j) ident[j] = j;
     return host_pipeline(ctx, (const void *const *)in_cols, LO_U8, nrows, k, nullptr, LO_U8, lo::kU8TileRows,
-                         (size_t)k * 256, counts, timing, [&](lo_table *tin, lo_table *, unsigned long long *cdev) {
-                             return hist_u8_impl(ctx, tin, ident.data(), k, (uint64_t *)cdev, ctx->stream);
+                         (size_t)k * 256, counts, timing, [&](lo_table *tin, lo_table *, unsigned long long *cdev, cudaStream_t cs) {
+                             return hist_u8_impl(ctx, tin, ident.data(), k, (uint64_t *)cdev, cs);
                          });
 }
 
@@ -931,9 +987,9 @@ int lo_value_counts_u32_host(lo_ctx *ctx, const uint32_t *codes, int64_t nrows, 
     // counts buffer layout: [ncodes counts][1 out-of-range flag]
     std::vector<uint64_t> tmp((size_t)ncodes + 1);
     int rc = host_pipeline(ctx, cols, LO_U32, nrows, 1, nullptr, LO_U32, 1 << 16, (size_t)ncodes + 1, tmp.data(), timing,
-                           [&](lo_table *tin, lo_table *, unsigned long long *cdev) {
+                           [&](lo_table *tin, lo_table *, unsigned long long *cdev, cudaStream_t cs) {
                                const int grid = ctx->sm_count * 8;
-                               lo::k_count_codes_u32<<<grid, 256, 0, ctx->stream>>>(
+                               lo::k_count_codes_u32<<<grid, 256, 0, cs>>>(
                                    (const uint32_t *)tin->base, tin->nrows, ncodes, cdev);
                                LO_CUDA(cudaGetLastError());
                                ctx->launches.fetch_add(1, std::memory_order_relaxed);
@@ -1124,9 +1180,9 @@ int lo_minmax_cast_host(lo_ctx *ctx, const double *const *in_cols, int64_t nrows
     // counts buffer layout per column: [ordered-uint min][ordered-uint max][count]
     std::vector<uint64_t> tmp((size_t)k * 3);
     int rc = host_pipeline(ctx, (const void *const *)in_cols, LO_F64, nrows, k, nullptr, LO_F32, lo::kTileRows,
-                           (size_t)k * 3, tmp.data(), timing, [&](lo_table *tin, lo_table *, unsigned long long *cdev) {
+                           (size_t)k * 3, tmp.data(), timing, [&](lo_table *tin, lo_table *, unsigned long long *cdev, cudaStream_t cs) {
                                dim3 grid((unsigned)std::min<int64_t>((tin->nrows + 2047) / 2048, ctx->sm_count * 4), (unsigned)k);
-                               lo::k_minmax_cast<<<grid, 256, 0, ctx->stream>>>(
+                               lo::k_minmax_cast<<<grid, 256, 0, cs>>>(
                                    (const char *)tin->base, tin->pitch, tin->nrows, cdev);
                                LO_CUDA(cudaGetLastError());
                                ctx->launches.fetch_add(1, std::memory_order_relaxed);

@@ -490,3 +490,35 @@ def test_download_waits_for_its_own_stream_only(engine):
     for t in (big, out, small):
         t.free()
     counts.free()
+
+
+def test_concurrent_host_calls_on_one_engine_overlap(engine):
+    """``*_host`` calls no longer queue behind one staging set: four threads (the REST services run a thread per job)
+    push different columns through one engine at once; every result is the oracle's."""
+    import threading
+    from oracle import cport
+    n = 1_500_000
+    jobs = []
+    for t in range(4):
+        cols = [cport.synth_f64(1, 77 + t, c, 0, n) for c in range(3)]
+        outs = [np.empty(n, np.float32) for _ in cols]
+        jobs.append((cols, outs))
+    lo, hi = np.full(3, -1000.0, np.float32), np.full(3, 1000.0, np.float32)
+    results, errors = [None] * 4, []
+
+    def run(i):
+        try:
+            results[i] = engine.project_cast_hist_host(jobs[i][0], 128, lo, hi, out=jobs[i][1])[0]
+        except Exception as exc:      # noqa: BLE001
+            errors.append(exc)
+    threads = [threading.Thread(target=run, args=(i,)) for i in range(4)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
+    for i, (cols, outs) in enumerate(jobs):
+        exp_out, exp_counts = cport.project_cast_hist(cols, 128, lo, hi)
+        np.testing.assert_array_equal(results[i], exp_counts)
+        for o, e in zip(outs, exp_out):
+            np.testing.assert_array_equal(o.view(np.uint32), e.view(np.uint32))
