@@ -874,7 +874,7 @@ __device__ __forceinline__ void bump_word(uint8_t *priv, uint32_t x, const U8Con
 // mode 7: the run test is taken once per BATCH of kU8Batch vectors (80 bytes per thread) instead of once per vector:
 // a constant column passes it for every batch, a mixed column pays 0.2 instead of 0.5 instructions per byte for it
 template <int MODE>
-__device__ __forceinline__ void bump_batch(uint8_t *priv, const uint4 (&v)[kU8Batch], const U8Consts &K) {
+__device__ __forceinline__ uint32_t bump_batch(uint8_t *priv, const uint4 (&v)[kU8Batch], const U8Consts &K) {
     const uint32_t splat = __byte_perm(v[0].x, 0, 0x0000);
     uint32_t diff = 0u;
 #pragma unroll
@@ -882,13 +882,14 @@ __device__ __forceinline__ void bump_batch(uint8_t *priv, const uint4 (&v)[kU8Ba
     if (__all_sync(__activemask(), diff == 0u)) {
         uint8_t *p = priv + bin_byte_offset(v[0].x & 0xFFu);
         *p = (uint8_t)(*p + 16 * kU8Batch);
-        return;
+        return 0u;
     }
 #pragma unroll
     for (int u = 0; u < kU8Batch; ++u) {
         bump_word<MODE>(priv, v[u].x, K); bump_word<MODE>(priv, v[u].y, K);
         bump_word<MODE>(priv, v[u].z, K); bump_word<MODE>(priv, v[u].w, K);
     }
+    return 1u;
 }
 
 // one 16-byte vector.  Run fast path: when every ACTIVE lane of the warp holds sixteen equal bytes
@@ -937,6 +938,7 @@ k_hist_u8_cols(const uint8_t *__restrict__ in_base, long long in_pitch, long lon
 #pragma unroll
         for (int u = 0; u < kU8Batch; ++u) v[0][u] = ldg128_stream(src + (long long)u * kThreads * kU8VecBytes);
         zero_private(smem, kHistRows);
+        uint32_t mixed = 0u, first = 0u;          // MODE 7: did any batch of this thread leave the run path / its first byte
 #pragma unroll
         for (int b = 0; b < kU8Batches; ++b) {
             if (b + 1 < kU8Batches) {
@@ -945,10 +947,29 @@ k_hist_u8_cols(const uint8_t *__restrict__ in_base, long long in_pitch, long lon
                     v[(b + 1) & 1][u] = ldg128_stream(src + (long long)((b + 1) * kU8Batch + u) * kThreads * kU8VecBytes);
             }
             if (MODE == 7) {
-                bump_batch<MODE>(priv, v[b & 1], K);
+                if (b == 0) first = v[0][0].x & 0xFFu;
+                mixed |= bump_batch<MODE>(priv, v[b & 1], K) | ((v[b & 1][0].x & 0xFFu) ^ first);
             } else {
 #pragma unroll
                 for (int u = 0; u < kU8Batch; ++u) bump_vec16<MODE>(priv, v[b & 1][u], K);
+            }
+        }
+        if (MODE == 7) {
+            // Constant tile (image borders, flags, padding: every byte of the 61 440 equal): nothing to fold — one RED
+            // of the tile's row count.  CTA-uniform decision: every thread stayed on the run path with one value of
+            // its own, then all those values are compared through one word of the (not yet used) fold scratch.
+            uint32_t *scratch = smem + kHistRows * kThreads;
+            if (__syncthreads_and(mixed == 0u)) {
+                if (threadIdx.x == 0) *scratch = first;
+                __syncthreads();
+                if (__syncthreads_and(first == *scratch)) {
+                    if (G.mode != 0) group_wait_generation(G);
+                    unsigned long long *dst = (G.mode == 0 ? counts : G.local) + (long long)j * 256 + first;
+                    if (threadIdx.x == 0)
+                        asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" :: "l"(dst), "l"((unsigned long long)kU8TileRows) : "memory");
+                    if (G.mode != 0) group_finish_column(G, j, 256, P.k, tiles_per_col, smem);
+                    return;
+                }
             }
         }
     } else if (ALIGNED) {
