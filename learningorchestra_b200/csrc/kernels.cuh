@@ -17,12 +17,15 @@
 //     LDS.U8 / IADD / STS.U8 (f64 kernel) or one ATOMS.ADD on the containing word (byte kernel) — no bank
 //     conflicts, and the cost is independent of the value distribution (a constant column is as fast as a
 //     uniform one).  A thread handles <= 255 elements per tile so a byte never wraps; the CTA then folds the 256
-//     private histograms with packed 16-bit adds + warp shuffles and issues one RED.64 per non-empty bin
-//     (system scope when the count matrix lives in a peer GPU's memory: the multi-GPU merge rides on the flush).
+//     private histograms (LDS.128, packed 16-bit adds, a transposing warp butterfly) and issues one RED.64 per
+//     non-empty bin.
+//   * several GPUs (GroupStep): the bins go to the device's own matrix; the CTA finishing a column's last tile pushes
+//     the column to the root GPU with system-scope RED.64 over NVLink, the last pusher arrives, the root's last CTA
+//     moves the merged matrix out — merge, arrival and epilogue ride inside the one streaming launch per step.
 //   * bin index = trunc(RN((x - lo) / w)) computed without a divide (hoisted reciprocal + two FMA
 //     corrections, proven and exhaustively self-tested equal to the IEEE quotient; bin_index_f32).
 //   * also here: k_parse_number (CPython float() on the GPU, parse_number.cuh), k_hash_count_f64 / _str
-//     (exact group-by), k_minmax_cast, the peer-merge flag kernels, generators, checksum.
+//     (exact group-by), k_minmax_cast, the group's small kernels (push, big-matrix merge, barrier), generators, checksum.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
