@@ -772,6 +772,7 @@ k_project_cast_hist_tma(const char *__restrict__ in_base, long long in_pitch,
 //   7: the counter word's whole shared-memory address from ONE PRMT (thread bits pre-merged into the row bytes), the
 //      field value from one wrap-mode funnel shift, the run test once per 80-byte batch: ~4.7 instead of ~6.3
 //      instructions per byte
+//   8: k_hist_u8_cols_wide — mode 7's arithmetic with 512 threads per CTA, two threads per private histogram (48 warps / SM)
 //   6: like 5 with the powers of two passed as kernel DATA so the shift-and-adds stay IMAD / IMAD.HI on the FMA
 //      pipe and only the masks and the final 1 << n are ALU-pipe work
 #ifndef LO_U8_MODE_DEFAULT
@@ -1013,6 +1014,154 @@ k_hist_u8_cols(const uint8_t *__restrict__ in_base, long long in_pitch, long lon
         fold_and_flush(smem, kHistRows, 256, G.local + (long long)j * 256);
         group_finish_column(G, j, 256, P.k, tiles_per_col, smem);
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4, wide form (LOEXEC_U8_MODE=8): 512 threads per CTA, TWO threads per private histogram.
+// The 256-thread kernel is latency-bound at the 24 warps per SM its 256 B of counters per thread allow (ncu: issue
+// slots 46 % busy, no pipe saturated).  Increments are shared-memory atomics anyway, so threads t and t + 256 —
+// different warps, same lane, hence the same private bank and still conflict-free inside every warp — can share one
+// histogram as long as the two together stay below 256 elements per tile: 7 vectors of 16 bytes each (2 x 112 = 224).
+// Same shared memory per CTA, twice the warps (48 per SM), half the registers per thread (<= 40).
+// ---------------------------------------------------------------------------------------------
+constexpr int kU8WThreads  = 512;
+constexpr int kU8WVecs     = 7;                                       // vectors per thread per tile
+constexpr int kU8WTileRows = kU8WThreads * kU8WVecs * kU8VecBytes;    // 57 344 bytes of one column
+
+// one run-tested batch of NV vectors for the shared-histogram kernel: everything is an atomic (the partner thread
+// may be updating the same word)
+template <int NV>
+__device__ __forceinline__ uint32_t bump_batch_shared(const uint4 (&v)[NV], uint32_t t4, uint32_t tidhi4) {
+    const uint32_t splat = __byte_perm(v[0].x, 0, 0x0000);
+    uint32_t diff = 0u;
+#pragma unroll
+    for (int u = 0; u < NV; ++u) diff |= (v[u].x ^ splat) | (v[u].y ^ splat) | (v[u].z ^ splat) | (v[u].w ^ splat);
+    if (__all_sync(__activemask(), diff == 0u)) {
+        const uint32_t b = v[0].x & 0xFFu;
+        atoms_add_base(((b & 0xFCu) << 8) | t4, (uint32_t)(16 * NV) << ((b & 3u) << 3));
+        return 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < NV; ++u) {
+        const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t rows   = (w[q] & 0xFCFCFCFCu) | tidhi4;
+            const uint32_t shifts = (w[q] & 0x03030303u) << 3;
+            atoms_add_base(__byte_perm(rows, t4, 0x7604u), one_shl_wrap(shifts));
+            atoms_add_base(__byte_perm(rows, t4, 0x7614u), one_shl_wrap(shifts >> 8));
+            atoms_add_base(__byte_perm(rows, t4, 0x7624u), one_shl_wrap(shifts >> 16));
+            atoms_add_base(__byte_perm(rows, t4, 0x7634u), one_shl_wrap(shifts >> 24));
+        }
+    }
+    return 1u;
+}
+
+// fold for 16 warps: warp wp owns rows wp, wp + 16, wp + 32, wp + 48 (8 packed registers, transposing butterfly over
+// lane bits 16 / 8 / 4, plain butterfly over bits 2 / 1)
+__device__ __forceinline__ void fold_and_flush_wide(uint32_t *smem, unsigned long long *counts) {
+    uint32_t *folded = smem + kHistRows * kThreads;   // 256 words
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    uint32_t r[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int w = warp + 16 * i;
+        const uint4 a = *reinterpret_cast<const uint4 *>(smem + w * kThreads + 4 * lane);
+        const uint4 b = *reinterpret_cast<const uint4 *>(smem + w * kThreads + 128 + 4 * lane);
+        const uint32_t x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        uint32_t even = 0u, odd = 0u;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            even += x[q] & 0x00FF00FFu;
+            odd  += __byte_perm(x[q], 0u, 0x4341u);
+        }
+        r[2 * i] = even;
+        r[2 * i + 1] = odd;
+    }
+#pragma unroll
+    for (int half = 4, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
+        const bool upper = (lane & bit) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const uint32_t send = upper ? r[i] : r[i + half];
+            const uint32_t keep = upper ? r[i + half] : r[i];
+            r[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+        }
+    }
+    uint32_t total = r[0] + __shfl_xor_sync(0xffffffffu, r[0], 2);
+    total += __shfl_xor_sync(0xffffffffu, total, 1);
+    if ((lane & 3) == 0) {
+        const int idx = (lane >> 2) & 7;
+        const int w = warp + 16 * (idx >> 1), parity = idx & 1;
+        folded[4 * w + parity]     = total & 0xFFFFu;
+        folded[4 * w + 2 + parity] = total >> 16;
+    }
+    __syncthreads();
+    if (threadIdx.x < 256) {
+        const uint32_t c = folded[threadIdx.x];
+        if (c) asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" :: "l"(counts + threadIdx.x), "l"((unsigned long long)c) : "memory");
+    }
+}
+
+__global__ void __launch_bounds__(kU8WThreads, 3)
+k_hist_u8_cols_wide(const uint8_t *__restrict__ in_base, long long in_pitch, long long nrows,
+                    unsigned tiles_per_col, unsigned long long *__restrict__ counts,
+                    const __grid_constant__ ColsU8 P, const __grid_constant__ GroupStep G) {
+    extern __shared__ uint32_t smem[];
+    if (G.overlap) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const unsigned j    = blockIdx.x / tiles_per_col;
+    const unsigned tile = blockIdx.x - j * tiles_per_col;
+    const long long r0  = (long long)tile * kU8WTileRows;
+    const long long n   = min((long long)kU8WTileRows, nrows - r0);
+    const uint8_t *in   = in_base + (long long)P.col[j] * in_pitch + r0;
+    const uint32_t t4 = 4u * (threadIdx.x & 255u);                       // byte offset of this thread's histogram column
+    const uint32_t tidhi4 = (t4 >> 8) * 0x01010101u;
+    if ((uint32_t)__cvta_generic_to_shared(smem) != LO_SMEM_WINDOW_BASE) __trap();     // immediate offset of the atomics
+    unsigned long long *dst = (G.mode == 0 ? counts : G.local) + (long long)j * 256;
+
+    auto clear = [&]() {
+        uint4 *p = reinterpret_cast<uint4 *>(smem);
+        for (int i = threadIdx.x; i < kHistRows * (kThreads / 4); i += kU8WThreads) p[i] = make_uint4(0u, 0u, 0u, 0u);
+        __syncthreads();
+    };
+
+    if (n == kU8WTileRows) {
+        uint4 va[4], vb[3];
+        const uint8_t *src = in + (long long)threadIdx.x * kU8VecBytes;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) va[u] = ldg128_stream(src + (long long)u * kU8WThreads * kU8VecBytes);
+        clear();                                                          // overlaps the first loads' DRAM latency
+#pragma unroll
+        for (int u = 0; u < 3; ++u) vb[u] = ldg128_stream(src + (long long)(4 + u) * kU8WThreads * kU8VecBytes);
+        const uint32_t first = va[0].x & 0xFFu;
+        uint32_t mixed = bump_batch_shared<4>(va, t4, tidhi4);
+        mixed |= bump_batch_shared<3>(vb, t4, tidhi4) | ((vb[0].x & 0xFFu) ^ first);
+        // constant tile: one RED of the tile's row count instead of the fold (see k_hist_u8_cols)
+        uint32_t *scratch = smem + kHistRows * kThreads;
+        if (__syncthreads_and(mixed == 0u)) {
+            if (threadIdx.x == 0) *scratch = first;
+            __syncthreads();
+            if (__syncthreads_and(first == *scratch)) {
+                if (G.mode != 0) group_wait_generation(G);
+                if (threadIdx.x == 0)
+                    asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" :: "l"(dst + first), "l"((unsigned long long)kU8WTileRows) : "memory");
+                if (G.mode != 0) group_finish_column(G, j, 256, P.k, tiles_per_col, smem);
+                return;
+            }
+        }
+    } else {
+        // ragged last tile of a column: byte by byte (atomics: the histogram is shared with the partner thread)
+        clear();
+#pragma unroll 1
+        for (long long e = threadIdx.x; e < n; e += kU8WThreads) {
+            const uint32_t b = ldg8_stream(in + e);
+            atoms_add_base(((b & 0xFCu) << 8) | t4, 1u << ((b & 3u) << 3));
+        }
+    }
+    if (G.mode != 0) group_wait_generation(G);
+    fold_and_flush_wide(smem, dst);
+    if (G.mode != 0) group_finish_column(G, j, 256, P.k, tiles_per_col, smem);
 }
 
 // ---------------------------------------------------------------------------------------------

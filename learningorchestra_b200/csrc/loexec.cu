@@ -189,6 +189,7 @@ int configure_kernels() {
     LO_TRY(allow_smem(lo::k_hist_u8_cols<true, 5>));
     LO_TRY(allow_smem(lo::k_hist_u8_cols<true, 6>));
     LO_TRY(allow_smem(lo::k_hist_u8_cols<true, 7>));
+    LO_TRY(allow_smem(lo::k_hist_u8_cols_wide));
     LO_TRY(allow_smem(lo::k_hist_u8_cols<false, 4>));
     return LO_OK;
 }
@@ -330,7 +331,11 @@ int hist_u8_impl(lo_ctx *ctx, const lo_table *in, const int32_t *col_idx, int32_
     if (in->nrows == 0 && !group) return LO_OK;
     const lo::GroupStep &G = group ? *group : kNoGroup;
     const bool aligned = ((uintptr_t)in->base % 16 == 0) && (in->pitch % 16 == 0);
-    const unsigned tiles_per_col = (unsigned)((in->nrows + lo::kU8TileRows - 1) / lo::kU8TileRows);
+    int mode = LO_U8_MODE_DEFAULT;
+    if (const char *e = getenv("LOEXEC_U8_MODE")) mode = atoi(e);       // measurement knob (scripts/u8_sweep.py)
+    const bool wide = aligned && mode == 8;
+    const int64_t tile_rows = wide ? lo::kU8WTileRows : lo::kU8TileRows;
+    const unsigned tiles_per_col = (unsigned)((in->nrows + tile_rows - 1) / tile_rows);
     for (int32_t c0 = 0; c0 < k; c0 += lo::kMaxColsU8) {
         lo::ColsU8 P;
         P.k = std::min<int32_t>(lo::kMaxColsU8, k - c0);
@@ -339,19 +344,19 @@ int hist_u8_impl(lo_ctx *ctx, const lo_table *in, const int32_t *col_idx, int32_
         const unsigned long long blocks = (unsigned long long)tiles_per_col * (unsigned)P.k;
         if (blocks > 0x7fffffffull) return fail(LO_ERR_INVALID, "table too large for one launch");
         unsigned long long *cnt = (unsigned long long *)counts_dev + (int64_t)c0 * 256;
-        int mode = LO_U8_MODE_DEFAULT;
-        if (const char *e = getenv("LOEXEC_U8_MODE")) mode = atoi(e);       // measurement knob (scripts/u8_sweep.py)
         const uint8_t *ib = (const uint8_t *)in->base;
         const long long ip = in->pitch, nr = in->nrows;
 #define LO_U8_LAUNCH(AL, MD)                                                                                      \
     LO_CUDA(launch_kernel(lo::k_hist_u8_cols<AL, MD>, (unsigned)blocks, lo::kThreads, (size_t)lo::kHistSmemBytes, s, \
                           G.overlap != 0, ib, ip, nr, tiles_per_col, cnt, P, G))
         if (!aligned)       LO_U8_LAUNCH(false, 4);
+        else if (wide)      LO_CUDA(launch_kernel(lo::k_hist_u8_cols_wide, (unsigned)blocks, lo::kU8WThreads, (size_t)lo::kHistSmemBytes, s,
+                                                  G.overlap != 0, ib, ip, nr, tiles_per_col, cnt, P, G));
         else if (mode == 2) LO_U8_LAUNCH(true, 2);
+        else if (mode == 4) LO_U8_LAUNCH(true, 4);
         else if (mode == 5) LO_U8_LAUNCH(true, 5);
         else if (mode == 6) LO_U8_LAUNCH(true, 6);
-        else if (mode == 7) LO_U8_LAUNCH(true, 7);
-        else                LO_U8_LAUNCH(true, 4);
+        else                LO_U8_LAUNCH(true, 7);
 #undef LO_U8_LAUNCH
         LO_CUDA(cudaGetLastError());
         ctx->launches.fetch_add(1, std::memory_order_relaxed);

@@ -147,6 +147,23 @@ def test_hist_u8_all_values_and_constant(engine):
     t.free()
 
 
+@pytest.mark.parametrize("mode", ["2", "4", "5", "6", "7", "8"])
+def test_hist_u8_every_kernel_variant(engine, monkeypatch, mode):
+    """Every selectable form of the byte-histogram kernel (LOEXEC_U8_MODE; 8 = the 512-thread shared-histogram kernel
+    with its own tile size) gives the oracle's counts: ragged sizes, full tiles, constant columns, every byte value."""
+    monkeypatch.setenv("LOEXEC_U8_MODE", mode)
+    wide_tile = 512 * 7 * 16
+    rng = np.random.default_rng(int(mode))
+    for nrows in (1, 17, 4097, TILE, TILE + 1, wide_tile, 2 * wide_tile + 777, 3 * TILE + 5):
+        table = np.stack([rng.integers(0, 256, nrows, dtype=np.uint8), np.full(nrows, 0, np.uint8), np.full(nrows, 200, np.uint8),
+                          np.arange(nrows, dtype=np.uint64).astype(np.uint8), bn.synth_u8(SEED, 300, 0, nrows),
+                          np.where(np.arange(nrows) < nrows // 2, 7, 9).astype(np.uint8)])
+        t = engine.table_from_numpy(table)
+        got = engine.hist_u8_cols(t, range(6)).to_numpy()
+        np.testing.assert_array_equal(got, bn.hist_u8_cols(table, range(6)), err_msg=f"mode {mode} nrows {nrows}")
+        t.free()
+
+
 def test_unaligned_wrapped_tables(engine):
     # foreign device memory with an odd element offset / pitch takes the scalar kernel variant
     nrows, ncols = 100_003, 3
