@@ -772,7 +772,8 @@ k_project_cast_hist_tma(const char *__restrict__ in_base, long long in_pitch,
 //   7: the counter word's whole shared-memory address from ONE PRMT (thread bits pre-merged into the row bytes), the
 //      field value from one wrap-mode funnel shift, the run test once per 80-byte batch: ~4.7 instead of ~6.3
 //      instructions per byte
-//   8: k_hist_u8_cols_wide — mode 7's arithmetic with 512 threads per CTA, two threads per private histogram (48 warps / SM)
+//   8 / 9: k_hist_u8_cols_wide<2 / 4> — mode 7's arithmetic with 512 / 1024 threads per CTA, two / four threads per
+//      private histogram (48 / 64 warps per SM)
 //   6: like 5 with the powers of two passed as kernel DATA so the shift-and-adds stay IMAD / IMAD.HI on the FMA
 //      pipe and only the masks and the final 1 << n are ALU-pipe work
 #ifndef LO_U8_MODE_DEFAULT
@@ -1024,9 +1025,18 @@ k_hist_u8_cols(const uint8_t *__restrict__ in_base, long long in_pitch, long lon
 // histogram as long as the two together stay below 256 elements per tile: 7 vectors of 16 bytes each (2 x 112 = 224).
 // Same shared memory per CTA, twice the warps (48 per SM), half the registers per thread (<= 40).
 // ---------------------------------------------------------------------------------------------
-constexpr int kU8WThreads  = 512;
-constexpr int kU8WVecs     = 7;                                       // vectors per thread per tile
-constexpr int kU8WTileRows = kU8WThreads * kU8WVecs * kU8VecBytes;    // 57 344 bytes of one column
+// TPH = threads per private histogram: 2 -> 512 threads x 7 vectors (224 elements per histogram), 3 CTAs / SM, 48 warps;
+//                                       4 -> 1024 threads x 3 vectors (192 elements), 2 CTAs / SM, 64 warps (<= 32 registers)
+template <int TPH> struct U8Wide {
+    static constexpr int kThreadsW  = 256 * TPH;
+    static constexpr int kVecs      = TPH == 2 ? 7 : 3;
+    static constexpr int kVecsA     = TPH == 2 ? 4 : 3;                       // first batch
+    static constexpr int kVecsB     = kVecs - kVecsA;                         // second batch (0 for TPH = 4)
+    static constexpr int kMinCtas   = TPH == 2 ? 3 : 2;
+    static constexpr int kTileRows  = kThreadsW * kVecs * kU8VecBytes;        // 57 344 / 49 152 bytes of one column
+    static_assert(TPH * kVecs * kU8VecBytes <= 255, "a byte counter must not wrap");
+};
+constexpr int kU8WTileRows2 = U8Wide<2>::kTileRows, kU8WTileRows4 = U8Wide<4>::kTileRows;
 
 // one run-tested batch of NV vectors for the shared-histogram kernel: everything is an atomic (the partner thread
 // may be updating the same word)
@@ -1057,16 +1067,18 @@ __device__ __forceinline__ uint32_t bump_batch_shared(const uint4 (&v)[NV], uint
     return 1u;
 }
 
-// fold for 16 warps: warp wp owns rows wp, wp + 16, wp + 32, wp + 48 (8 packed registers, transposing butterfly over
-// lane bits 16 / 8 / 4, plain butterfly over bits 2 / 1)
+// fold for NW = 16 or 32 warps: warp wp owns rows wp, wp + NW, ... (64 / NW rows -> R = 128 / NW packed registers);
+// transposing butterfly over the top log2(R) lane bits, plain butterfly over the rest
+template <int NW>
 __device__ __forceinline__ void fold_and_flush_wide(uint32_t *smem, unsigned long long *counts) {
+    constexpr int kRowsPerWarp = kHistRows / NW, R = 2 * kRowsPerWarp;        // NW 16 -> 4 rows, R 8 ; NW 32 -> 2 rows, R 4
     uint32_t *folded = smem + kHistRows * kThreads;   // 256 words
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     __syncthreads();
-    uint32_t r[8];
+    uint32_t r[R];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int w = warp + 16 * i;
+    for (int i = 0; i < kRowsPerWarp; ++i) {
+        const int w = warp + NW * i;
         const uint4 a = *reinterpret_cast<const uint4 *>(smem + w * kThreads + 4 * lane);
         const uint4 b = *reinterpret_cast<const uint4 *>(smem + w * kThreads + 128 + 4 * lane);
         const uint32_t x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
@@ -1079,8 +1091,9 @@ __device__ __forceinline__ void fold_and_flush_wide(uint32_t *smem, unsigned lon
         r[2 * i] = even;
         r[2 * i + 1] = odd;
     }
+    int bit = 16;
 #pragma unroll
-    for (int half = 4, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
+    for (int half = R / 2; half >= 1; half >>= 1, bit >>= 1) {
         const bool upper = (lane & bit) != 0;
 #pragma unroll
         for (int i = 0; i < half; ++i) {
@@ -1089,11 +1102,13 @@ __device__ __forceinline__ void fold_and_flush_wide(uint32_t *smem, unsigned lon
             r[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
         }
     }
-    uint32_t total = r[0] + __shfl_xor_sync(0xffffffffu, r[0], 2);
-    total += __shfl_xor_sync(0xffffffffu, total, 1);
-    if ((lane & 3) == 0) {
-        const int idx = (lane >> 2) & 7;
-        const int w = warp + 16 * (idx >> 1), parity = idx & 1;
+    uint32_t total = r[0];
+    constexpr int kPlainBits = 32 / R;                   // lanes that still hold partial sums of the same register
+#pragma unroll
+    for (int s2 = kPlainBits / 2; s2 >= 1; s2 >>= 1) total += __shfl_xor_sync(0xffffffffu, total, s2);
+    if ((lane & (kPlainBits - 1)) == 0) {
+        const int idx = (lane / kPlainBits) & (R - 1);
+        const int w = warp + NW * (idx >> 1), parity = idx & 1;
         folded[4 * w + parity]     = total & 0xFFFFu;
         folded[4 * w + 2 + parity] = total >> 16;
     }
@@ -1104,16 +1119,18 @@ __device__ __forceinline__ void fold_and_flush_wide(uint32_t *smem, unsigned lon
     }
 }
 
-__global__ void __launch_bounds__(kU8WThreads, 3)
+template <int TPH>
+__global__ void __launch_bounds__(U8Wide<TPH>::kThreadsW, U8Wide<TPH>::kMinCtas)
 k_hist_u8_cols_wide(const uint8_t *__restrict__ in_base, long long in_pitch, long long nrows,
                     unsigned tiles_per_col, unsigned long long *__restrict__ counts,
                     const __grid_constant__ ColsU8 P, const __grid_constant__ GroupStep G) {
+    using W = U8Wide<TPH>;
     extern __shared__ uint32_t smem[];
     if (G.overlap) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const unsigned j    = blockIdx.x / tiles_per_col;
     const unsigned tile = blockIdx.x - j * tiles_per_col;
-    const long long r0  = (long long)tile * kU8WTileRows;
-    const long long n   = min((long long)kU8WTileRows, nrows - r0);
+    const long long r0  = (long long)tile * W::kTileRows;
+    const long long n   = min((long long)W::kTileRows, nrows - r0);
     const uint8_t *in   = in_base + (long long)P.col[j] * in_pitch + r0;
     const uint32_t t4 = 4u * (threadIdx.x & 255u);                       // byte offset of this thread's histogram column
     const uint32_t tidhi4 = (t4 >> 8) * 0x01010101u;
@@ -1122,21 +1139,27 @@ k_hist_u8_cols_wide(const uint8_t *__restrict__ in_base, long long in_pitch, lon
 
     auto clear = [&]() {
         uint4 *p = reinterpret_cast<uint4 *>(smem);
-        for (int i = threadIdx.x; i < kHistRows * (kThreads / 4); i += kU8WThreads) p[i] = make_uint4(0u, 0u, 0u, 0u);
+        for (int i = threadIdx.x; i < kHistRows * (kThreads / 4); i += W::kThreadsW) p[i] = make_uint4(0u, 0u, 0u, 0u);
         __syncthreads();
     };
 
-    if (n == kU8WTileRows) {
-        uint4 va[4], vb[3];
+    if (n == W::kTileRows) {
+        uint4 va[W::kVecsA];
         const uint8_t *src = in + (long long)threadIdx.x * kU8VecBytes;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) va[u] = ldg128_stream(src + (long long)u * kU8WThreads * kU8VecBytes);
+        for (int u = 0; u < W::kVecsA; ++u) va[u] = ldg128_stream(src + (long long)u * W::kThreadsW * kU8VecBytes);
         clear();                                                          // overlaps the first loads' DRAM latency
-#pragma unroll
-        for (int u = 0; u < 3; ++u) vb[u] = ldg128_stream(src + (long long)(4 + u) * kU8WThreads * kU8VecBytes);
         const uint32_t first = va[0].x & 0xFFu;
-        uint32_t mixed = bump_batch_shared<4>(va, t4, tidhi4);
-        mixed |= bump_batch_shared<3>(vb, t4, tidhi4) | ((vb[0].x & 0xFFu) ^ first);
+        uint32_t mixed;
+        if (W::kVecsB > 0) {
+            uint4 vb[W::kVecsB > 0 ? W::kVecsB : 1];
+#pragma unroll
+            for (int u = 0; u < W::kVecsB; ++u) vb[u] = ldg128_stream(src + (long long)(W::kVecsA + u) * W::kThreadsW * kU8VecBytes);
+            mixed = bump_batch_shared<W::kVecsA>(va, t4, tidhi4);
+            mixed |= bump_batch_shared<(W::kVecsB > 0 ? W::kVecsB : 1)>(vb, t4, tidhi4) | ((vb[0].x & 0xFFu) ^ first);
+        } else {
+            mixed = bump_batch_shared<W::kVecsA>(va, t4, tidhi4);
+        }
         // constant tile: one RED of the tile's row count instead of the fold (see k_hist_u8_cols)
         uint32_t *scratch = smem + kHistRows * kThreads;
         if (__syncthreads_and(mixed == 0u)) {
@@ -1145,22 +1168,22 @@ k_hist_u8_cols_wide(const uint8_t *__restrict__ in_base, long long in_pitch, lon
             if (__syncthreads_and(first == *scratch)) {
                 if (G.mode != 0) group_wait_generation(G);
                 if (threadIdx.x == 0)
-                    asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" :: "l"(dst + first), "l"((unsigned long long)kU8WTileRows) : "memory");
+                    asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" :: "l"(dst + first), "l"((unsigned long long)W::kTileRows) : "memory");
                 if (G.mode != 0) group_finish_column(G, j, 256, P.k, tiles_per_col, smem);
                 return;
             }
         }
     } else {
-        // ragged last tile of a column: byte by byte (atomics: the histogram is shared with the partner thread)
+        // ragged last tile of a column: byte by byte (atomics: the histogram is shared with the partner threads)
         clear();
 #pragma unroll 1
-        for (long long e = threadIdx.x; e < n; e += kU8WThreads) {
+        for (long long e = threadIdx.x; e < n; e += W::kThreadsW) {
             const uint32_t b = ldg8_stream(in + e);
             atoms_add_base(((b & 0xFCu) << 8) | t4, 1u << ((b & 3u) << 3));
         }
     }
     if (G.mode != 0) group_wait_generation(G);
-    fold_and_flush_wide(smem, dst);
+    fold_and_flush_wide<W::kThreadsW / 32>(smem, dst);
     if (G.mode != 0) group_finish_column(G, j, 256, P.k, tiles_per_col, smem);
 }
 

@@ -189,7 +189,8 @@ int configure_kernels() {
     LO_TRY(allow_smem(lo::k_hist_u8_cols<true, 5>));
     LO_TRY(allow_smem(lo::k_hist_u8_cols<true, 6>));
     LO_TRY(allow_smem(lo::k_hist_u8_cols<true, 7>));
-    LO_TRY(allow_smem(lo::k_hist_u8_cols_wide));
+    LO_TRY(allow_smem(lo::k_hist_u8_cols_wide<2>));
+    LO_TRY(allow_smem(lo::k_hist_u8_cols_wide<4>));
     LO_TRY(allow_smem(lo::k_hist_u8_cols<false, 4>));
     return LO_OK;
 }
@@ -333,8 +334,8 @@ int hist_u8_impl(lo_ctx *ctx, const lo_table *in, const int32_t *col_idx, int32_
     const bool aligned = ((uintptr_t)in->base % 16 == 0) && (in->pitch % 16 == 0);
     int mode = LO_U8_MODE_DEFAULT;
     if (const char *e = getenv("LOEXEC_U8_MODE")) mode = atoi(e);       // measurement knob (scripts/u8_sweep.py)
-    const bool wide = aligned && mode == 8;
-    const int64_t tile_rows = wide ? lo::kU8WTileRows : lo::kU8TileRows;
+    const bool wide = aligned && (mode == 8 || mode == 9);
+    const int64_t tile_rows = !wide ? lo::kU8TileRows : mode == 8 ? lo::kU8WTileRows2 : lo::kU8WTileRows4;
     const unsigned tiles_per_col = (unsigned)((in->nrows + tile_rows - 1) / tile_rows);
     for (int32_t c0 = 0; c0 < k; c0 += lo::kMaxColsU8) {
         lo::ColsU8 P;
@@ -350,7 +351,9 @@ int hist_u8_impl(lo_ctx *ctx, const lo_table *in, const int32_t *col_idx, int32_
     LO_CUDA(launch_kernel(lo::k_hist_u8_cols<AL, MD>, (unsigned)blocks, lo::kThreads, (size_t)lo::kHistSmemBytes, s, \
                           G.overlap != 0, ib, ip, nr, tiles_per_col, cnt, P, G))
         if (!aligned)       LO_U8_LAUNCH(false, 4);
-        else if (wide)      LO_CUDA(launch_kernel(lo::k_hist_u8_cols_wide, (unsigned)blocks, lo::kU8WThreads, (size_t)lo::kHistSmemBytes, s,
+        else if (mode == 8) LO_CUDA(launch_kernel(lo::k_hist_u8_cols_wide<2>, (unsigned)blocks, 512u, (size_t)lo::kHistSmemBytes, s,
+                                                  G.overlap != 0, ib, ip, nr, tiles_per_col, cnt, P, G));
+        else if (mode == 9) LO_CUDA(launch_kernel(lo::k_hist_u8_cols_wide<4>, (unsigned)blocks, 1024u, (size_t)lo::kHistSmemBytes, s,
                                                   G.overlap != 0, ib, ip, nr, tiles_per_col, cnt, P, G));
         else if (mode == 2) LO_U8_LAUNCH(true, 2);
         else if (mode == 4) LO_U8_LAUNCH(true, 4);

@@ -147,12 +147,12 @@ def test_hist_u8_all_values_and_constant(engine):
     t.free()
 
 
-@pytest.mark.parametrize("mode", ["2", "4", "5", "6", "7", "8"])
+@pytest.mark.parametrize("mode", ["2", "4", "5", "6", "7", "8", "9"])
 def test_hist_u8_every_kernel_variant(engine, monkeypatch, mode):
     """Every selectable form of the byte-histogram kernel (LOEXEC_U8_MODE; 8 = the 512-thread shared-histogram kernel
     with its own tile size) gives the oracle's counts: ragged sizes, full tiles, constant columns, every byte value."""
     monkeypatch.setenv("LOEXEC_U8_MODE", mode)
-    wide_tile = 512 * 7 * 16
+    wide_tile = 512 * 7 * 16 if mode != "9" else 1024 * 3 * 16
     rng = np.random.default_rng(int(mode))
     for nrows in (1, 17, 4097, TILE, TILE + 1, wide_tile, 2 * wide_tile + 777, 3 * TILE + 5):
         table = np.stack([rng.integers(0, 256, nrows, dtype=np.uint8), np.full(nrows, 0, np.uint8), np.full(nrows, 200, np.uint8),
