@@ -988,14 +988,28 @@ k_hist_u8_cols(const uint8_t *__restrict__ in_base, long long in_pitch, long lon
 #pragma unroll
                 for (int u = 0; u < kU8Batch; ++u) v[u] = ldg128_stream(in + e0 + (long long)u * kThreads * kU8VecBytes);
 #pragma unroll
-                for (int u = 0; u < kU8Batch; ++u) bump_vec16<MODE>(priv, v[u], K);
+                for (int u = 0; u < kU8Batch; ++u) bump_vec16<MODE == 7 ? 4 : MODE>(priv, v[u], K);
             } else {
-#pragma unroll 1
+                // the batch straddles the end of the column: whole 16-byte vectors still go through the vector path
+                // (all loads of the batch in flight together), only the last partial vector is read byte by byte.
+                // bump_vec16's warp vote is taken over the active lanes, so the divergence here is safe.
+                uint4 v[kU8Batch];
+                bool whole[kU8Batch];
+#pragma unroll
                 for (int u = 0; u < kU8Batch; ++u) {
                     const long long e = e0 + (long long)u * kThreads * kU8VecBytes;
+                    whole[u] = e + kU8VecBytes <= n;
+                    if (whole[u]) v[u] = ldg128_stream(in + e);
+                }
+#pragma unroll
+                for (int u = 0; u < kU8Batch; ++u) {
+                    const long long e = e0 + (long long)u * kThreads * kU8VecBytes;
+                    if (whole[u]) {
+                        bump_vec16<MODE == 7 ? 4 : MODE>(priv, v[u], K);
+                    } else if (e < n) {
 #pragma unroll 1
-                    for (int q = 0; q < kU8VecBytes; ++q)
-                        if (e + q < n) bump(priv, ldg8_stream(in + e + q));
+                        for (int q = 0; q < kU8VecBytes && e + q < n; ++q) bump(priv, ldg8_stream(in + e + q));
+                    }
                 }
             }
         }
