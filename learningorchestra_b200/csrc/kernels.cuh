@@ -819,6 +819,12 @@ __device__ __forceinline__ void atoms_add_base(uint32_t offset, uint32_t v) {
 }
 static_assert(LO_SMEM_WINDOW_BASE == 1024, "keep the immediate in atoms_add_base in sync");
 
+__device__ __forceinline__ uint32_t mul_wide_hi(uint32_t a, uint32_t b) {       // (a * b) >> 32 through IMAD.WIDE.U32
+    unsigned long long d;
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(d) : "r"(a), "r"(b));
+    return (uint32_t)(d >> 32);
+}
+
 struct U8Consts { uint32_t p8, p11, p16, p19, p24, p27, p3; };
 
 template <int MODE>
@@ -837,7 +843,7 @@ __device__ __forceinline__ void bump_word(uint8_t *priv, uint32_t x, const U8Con
             const uint32_t sh  = __byte_perm(shifts, 0u, 0x4440u | (uint32_t)q);          // byte q moved to bits 0..7
             atomicAdd(reinterpret_cast<uint32_t *>(priv + off), 1u << sh);
         }
-    } else if (MODE == 7) {
+    } else if (MODE == 7 || MODE == 10) {
         // The counter word's offset inside the histogram in ONE PRMT.  The word of thread t for byte value b is at
         // (b >> 2) * 1024 + 4 * t from the start of the dynamic shared memory, i.e. byte by byte
         //     [ (4t) & 0xFF | (b & 0xFC) + ((4t) >> 8) | 0 | 0 ];
@@ -849,10 +855,20 @@ __device__ __forceinline__ void bump_word(uint8_t *priv, uint32_t x, const U8Con
         const uint32_t t4 = K.p3;                                                   // 4 * t
         const uint32_t rows   = (x & 0xFCFCFCFCu) | K.p8;
         const uint32_t shifts = (x & 0x03030303u) << 3;
-        atoms_add_base(__byte_perm(rows, t4, 0x7604u), one_shl_wrap(shifts));       // byte 0 of x
-        atoms_add_base(__byte_perm(rows, t4, 0x7614u), one_shl_wrap(shifts >> 8));
-        atoms_add_base(__byte_perm(rows, t4, 0x7624u), one_shl_wrap(shifts >> 16));
-        atoms_add_base(__byte_perm(rows, t4, 0x7634u), one_shl_wrap(shifts >> 24));
+        if (MODE == 10) {
+            // mode 10: the three count extractions as the HIGH word of a widening multiply by 2^24 / 2^16 / 2^8 held as
+            // DATA (so ptxas cannot turn them back into SHF): FMA pipe instead of ALU pipe (scripts/probes/atoms_probe:
+            // the ALU pipe's 64 lane-ops per clock per SM, not the atomics, is what the per-byte arithmetic runs into)
+            atoms_add_base(__byte_perm(rows, t4, 0x7604u), one_shl_wrap(shifts));
+            atoms_add_base(__byte_perm(rows, t4, 0x7614u), one_shl_wrap(mul_wide_hi(shifts, K.p24)));
+            atoms_add_base(__byte_perm(rows, t4, 0x7624u), one_shl_wrap(mul_wide_hi(shifts, K.p16)));
+            atoms_add_base(__byte_perm(rows, t4, 0x7634u), one_shl_wrap(mul_wide_hi(shifts, K.p11)));
+        } else {
+            atoms_add_base(__byte_perm(rows, t4, 0x7604u), one_shl_wrap(shifts));       // byte 0 of x
+            atoms_add_base(__byte_perm(rows, t4, 0x7614u), one_shl_wrap(shifts >> 8));
+            atoms_add_base(__byte_perm(rows, t4, 0x7624u), one_shl_wrap(shifts >> 16));
+            atoms_add_base(__byte_perm(rows, t4, 0x7634u), one_shl_wrap(shifts >> 24));
+        }
     } else {
         // counter word of byte q (value b): priv + (b >> 2) * 1024; field at bit 8 * (b & 3).  Address =
         // (x & mask_q) * 2^s + priv, shift count = (x & 0x03030303) moved to bits 3..4 (SHF.L.W reads bits 0..4 only)
@@ -929,8 +945,9 @@ k_hist_u8_cols(const uint8_t *__restrict__ in_base, long long in_pitch, long lon
     const uint8_t *in   = in_base + (long long)P.col[j] * in_pitch + r0;
     uint8_t *priv = reinterpret_cast<uint8_t *>(smem) + 4 * threadIdx.x;
     U8Consts K = {P.p8, P.p11, P.p16, P.p19, P.p24, P.p27, P.p3};
-    if (MODE == 7) {
+    if (MODE == 7 || MODE == 10) {
         if ((uint32_t)__cvta_generic_to_shared(smem) != LO_SMEM_WINDOW_BASE) __trap();    // mode 7's immediate offset
+        K.p11 = K.p8;                              // 2^8 as data (mode 10's >> 24)
         K.p3 = 4u * threadIdx.x;
         K.p8 = ((4u * threadIdx.x) >> 8) * 0x01010101u;
     }
@@ -951,7 +968,7 @@ k_hist_u8_cols(const uint8_t *__restrict__ in_base, long long in_pitch, long lon
                 for (int u = 0; u < kU8Batch; ++u)
                     v[(b + 1) & 1][u] = ldg128_stream(src + (long long)((b + 1) * kU8Batch + u) * kThreads * kU8VecBytes);
             }
-            if (MODE == 7) {
+            if (MODE == 7 || MODE == 10) {
                 if (b == 0) first = v[0][0].x & 0xFFu;
                 mixed |= bump_batch<MODE>(priv, v[b & 1], K) | ((v[b & 1][0].x & 0xFFu) ^ first);
             } else {
@@ -959,7 +976,7 @@ k_hist_u8_cols(const uint8_t *__restrict__ in_base, long long in_pitch, long lon
                 for (int u = 0; u < kU8Batch; ++u) bump_vec16<MODE>(priv, v[b & 1][u], K);
             }
         }
-        if (MODE == 7) {
+        if (MODE == 7 || MODE == 10) {
             // Constant tile (image borders, flags, padding: every byte of the 61 440 equal): nothing to fold — one RED
             // of the tile's row count.  CTA-uniform decision: every thread stayed on the run path with one value of
             // its own, then all those values are compared through one word of the (not yet used) fold scratch.
@@ -988,7 +1005,7 @@ k_hist_u8_cols(const uint8_t *__restrict__ in_base, long long in_pitch, long lon
 #pragma unroll
                 for (int u = 0; u < kU8Batch; ++u) v[u] = ldg128_stream(in + e0 + (long long)u * kThreads * kU8VecBytes);
 #pragma unroll
-                for (int u = 0; u < kU8Batch; ++u) bump_vec16<MODE == 7 ? 4 : MODE>(priv, v[u], K);
+                for (int u = 0; u < kU8Batch; ++u) bump_vec16<(MODE == 7 || MODE == 10) ? 4 : MODE>(priv, v[u], K);
             } else {
                 // the batch straddles the end of the column: whole 16-byte vectors still go through the vector path
                 // (all loads of the batch in flight together), only the last partial vector is read byte by byte.
@@ -1005,7 +1022,7 @@ k_hist_u8_cols(const uint8_t *__restrict__ in_base, long long in_pitch, long lon
                 for (int u = 0; u < kU8Batch; ++u) {
                     const long long e = e0 + (long long)u * kThreads * kU8VecBytes;
                     if (whole[u]) {
-                        bump_vec16<MODE == 7 ? 4 : MODE>(priv, v[u], K);
+                        bump_vec16<(MODE == 7 || MODE == 10) ? 4 : MODE>(priv, v[u], K);
                     } else if (e < n) {
 #pragma unroll 1
                         for (int q = 0; q < kU8VecBytes && e + q < n; ++q) bump(priv, ldg8_stream(in + e + q));

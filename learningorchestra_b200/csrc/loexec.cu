@@ -189,6 +189,7 @@ int configure_kernels() {
     LO_TRY(allow_smem(lo::k_hist_u8_cols<true, 5>));
     LO_TRY(allow_smem(lo::k_hist_u8_cols<true, 6>));
     LO_TRY(allow_smem(lo::k_hist_u8_cols<true, 7>));
+    LO_TRY(allow_smem(lo::k_hist_u8_cols<true, 10>));
     LO_TRY(allow_smem(lo::k_hist_u8_cols_wide<2>));
     LO_TRY(allow_smem(lo::k_hist_u8_cols_wide<4>));
     LO_TRY(allow_smem(lo::k_hist_u8_cols<false, 4>));
@@ -359,6 +360,7 @@ int hist_u8_impl(lo_ctx *ctx, const lo_table *in, const int32_t *col_idx, int32_
         else if (mode == 4) LO_U8_LAUNCH(true, 4);
         else if (mode == 5) LO_U8_LAUNCH(true, 5);
         else if (mode == 6) LO_U8_LAUNCH(true, 6);
+        else if (mode == 10) LO_U8_LAUNCH(true, 10);
         else                LO_U8_LAUNCH(true, 7);
 #undef LO_U8_LAUNCH
         LO_CUDA(cudaGetLastError());

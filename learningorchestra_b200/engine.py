@@ -30,8 +30,17 @@ def _stream_ptr(stream) -> C.c_void_p:
 
 
 def _i32(col_idx: Iterable[int]):
+    """ctypes int32 array of the column indices; an array made by :func:`prepare_columns` is passed through (building
+    it costs ~0.1 us per column in Python — 80 us for the 784 columns of config M, more than the kernel at 8 GPUs)."""
+    if isinstance(col_idx, C.Array):
+        return col_idx, len(col_idx)
     idx = [int(c) for c in col_idx]
     return (C.c_int32 * len(idx))(*idx), len(idx)
+
+
+def prepare_columns(col_idx: Iterable[int]):
+    """Column indices converted once, for callers that issue the same request many times."""
+    return _i32(col_idx)[0]
 
 
 class DeviceCounts:
