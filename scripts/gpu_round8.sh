@@ -4,9 +4,11 @@
 TAG=${1:-r}
 mkdir -p gpurun_out
 nvidia-smi topo -m > gpurun_out/topo_$TAG.txt 2>&1
+if [[ "$*" != *notests* ]]; then
 timeout 600 python -m pytest "tests/test_gpu_group.py::test_local_group_over_all_visible_devices" \
     "tests/test_gpu_executors.py::test_rest_binned_histogram_shards_over_every_visible_gpu" \
     "tests/test_gpu_group.py::test_rank_group_nccl_merge_equals_oracle" -x -q 2>&1 | tail -6 | tee gpurun_out/pytest_group_$TAG.txt
+fi
 run() {  # name, ngpus, extra args...
   local name=$1 n=$2; shift 2
   if [ "$n" = 1 ]; then
@@ -26,5 +28,7 @@ run s100_n4 4 --workload s100 --no-e2e
 run s100_n2 2 --workload s100 --no-e2e
 run s100_n1 1 --workload s100 --no-e2e --no-cpu --executor-rows 0
 run m_n1 1 --workload m --no-e2e --no-cpu
+if [[ "$*" != *noref* ]]; then
 timeout 300 python bench.py --impl reference --gpus 8 --steps 3 --warmup 1 > gpurun_out/bench_ref_$TAG.json 2> gpurun_out/bench_ref_$TAG.err
 echo "rc=$? reference arm"; cut -c1-900 gpurun_out/bench_ref_$TAG.json
+fi
