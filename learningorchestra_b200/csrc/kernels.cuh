@@ -772,6 +772,7 @@ k_project_cast_hist_tma(const char *__restrict__ in_base, long long in_pitch,
 //   7: the counter word's whole shared-memory address from ONE PRMT (thread bits pre-merged into the row bytes), the
 //      field value from one wrap-mode funnel shift, the run test once per 80-byte batch: ~4.7 instead of ~6.3
 //      instructions per byte
+//   11: k_hist_u8_cols_lanes — 32-bit counters in 64 lane slots shared by all warps of the CTA: one PRMT + one ATOMS per byte
 //   8 / 9: k_hist_u8_cols_wide<2 / 4> — mode 7's arithmetic with 512 / 1024 threads per CTA, two / four threads per
 //      private histogram (48 / 64 warps per SM)
 //   6: like 5 with the powers of two passed as kernel DATA so the shift-and-adds stay IMAD / IMAD.HI on the FMA
@@ -1216,6 +1217,105 @@ k_hist_u8_cols_wide(const uint8_t *__restrict__ in_base, long long in_pitch, lon
     if (G.mode != 0) group_wait_generation(G);
     fold_and_flush_wide<W::kThreadsW / 32>(smem, dst);
     if (G.mode != 0) group_finish_column(G, j, 256, P.k, tiles_per_col, smem);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4, lane-slot form (LOEXEC_U8_MODE=11): 32-bit counters shared by all warps of the CTA.
+// scripts/probes/atoms_probe measured what bounds the per-thread byte counters: not the atomic unit (1.58 conflict-free
+// ATOMS per clock per SM with operands ready) but the arithmetic that turns a byte into (counter word, byte field):
+// mask, PRMT, shift extraction, 1 << n.  This layout needs none of it.  The CTA keeps ONE histogram of 256 bins x 64
+// slots of 32-bit counters (64 KiB): slot = lane + 32 * (warp & 1), counter of (bin b, slot s) at byte b * 256 + 4 * s.
+//   * bank = (b * 64 + s) mod 32 = lane: every warp instruction is conflict-free, whatever the data;
+//   * the address of a byte's counter is [4s | b | 0 | 0] byte by byte: ONE PRMT straight from the input word — no mask,
+//     no field shift; the increment is the constant 1;
+//   * warps of equal parity share counters through the atomics (different warps never collide inside one instruction);
+//   * 32-bit counters do not wrap, so a CTA streams a long chunk of its column (up to 256 Ki rows) and folds once:
+//     thread t sums the 64 slots of bin t (rotated start: conflict-free) and issues one RED.64.
+// Per byte: one PRMT + one ATOMS.ADD (+ 1/4 of a LOP3 for the run test).
+// ---------------------------------------------------------------------------------------------
+constexpr int kU8LThreads   = 512;
+constexpr int kU8LSmemBytes = 256 * 64 * 4;                       // 64 KiB
+constexpr int kU8LRoundRows = kU8LThreads * 4 * kU8VecBytes;      // 32 768 rows per loop iteration (4 vectors per thread)
+
+__global__ void __launch_bounds__(kU8LThreads, 3)
+k_hist_u8_cols_lanes(const uint8_t *__restrict__ in_base, long long in_pitch, long long nrows,
+                     unsigned chunks_per_col, long long chunk_rows, unsigned long long *__restrict__ counts,
+                     const __grid_constant__ ColsU8 P, const __grid_constant__ GroupStep G) {
+    extern __shared__ uint32_t smem[];
+    if (G.overlap) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const unsigned j     = blockIdx.x / chunks_per_col;
+    const unsigned chunk = blockIdx.x - j * chunks_per_col;
+    const long long r0   = (long long)chunk * chunk_rows;
+    const long long n    = min(chunk_rows, nrows - r0);
+    const uint8_t *in    = in_base + (long long)P.col[j] * in_pitch + r0;
+    if ((uint32_t)__cvta_generic_to_shared(smem) != LO_SMEM_WINDOW_BASE) __trap();     // immediate offset of the atomics
+    const uint32_t slot4 = 4u * ((threadIdx.x & 31u) + 32u * ((threadIdx.x >> 5) & 1u));
+    const uint32_t one = 1u;
+    const uint8_t *src = in + (long long)threadIdx.x * kU8VecBytes;
+
+    uint4 v[4];
+    const bool have_round = n >= kU8LRoundRows;
+    if (have_round) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = ldg128_stream(src + (long long)u * kU8LThreads * kU8VecBytes);
+    }
+    {   // clear the counters (overlaps the first loads' DRAM latency)
+        uint4 *p = reinterpret_cast<uint4 *>(smem);
+        for (int i = threadIdx.x; i < kU8LSmemBytes / 16; i += kU8LThreads) p[i] = make_uint4(0u, 0u, 0u, 0u);
+        __syncthreads();
+    }
+    auto count_vec = [&](const uint4 &x) {
+        const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            atoms_add_base(__byte_perm(w[q], slot4, 0x6504u), one);
+            atoms_add_base(__byte_perm(w[q], slot4, 0x6514u), one);
+            atoms_add_base(__byte_perm(w[q], slot4, 0x6524u), one);
+            atoms_add_base(__byte_perm(w[q], slot4, 0x6534u), one);
+        }
+    };
+    long long done = 0;
+#pragma unroll 1
+    for (; done + kU8LRoundRows <= n; done += kU8LRoundRows) {
+        uint4 cur[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) cur[u] = v[u];
+        if (done + 2 * (long long)kU8LRoundRows <= n) {            // next round's loads in flight while this one is counted
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = ldg128_stream(src + done + kU8LRoundRows + (long long)u * kU8LThreads * kU8VecBytes);
+        }
+        const uint32_t splat = __byte_perm(cur[0].x, 0, 0x0000);
+        uint32_t diff = 0u;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) diff |= (cur[u].x ^ splat) | (cur[u].y ^ splat) | (cur[u].z ^ splat) | (cur[u].w ^ splat);
+        if (__all_sync(0xffffffffu, diff == 0u)) {                 // run of one value (constant columns): one atomic for 64 bytes
+            atoms_add_base(((cur[0].x & 0xFFu) << 8) | slot4, 64u);
+        } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) count_vec(cur[u]);
+        }
+    }
+    // rest of the chunk: whole vectors, then single bytes
+#pragma unroll 1
+    for (long long e = done + (long long)threadIdx.x * kU8VecBytes; e < n; e += (long long)kU8LThreads * kU8VecBytes) {
+        if (e + kU8VecBytes <= n) {
+            count_vec(ldg128_stream(in + e));
+        } else {
+#pragma unroll 1
+            for (long long q = e; q < n; ++q) atoms_add_base((ldg8_stream(in + q) << 8) | slot4, one);
+        }
+    }
+    __syncthreads();
+    if (G.mode != 0) group_wait_generation(G);
+    if (threadIdx.x < 256) {
+        const uint32_t *row = smem + threadIdx.x * 64;
+        unsigned long long c = 0;
+#pragma unroll 8
+        for (int i = 0; i < 64; ++i) c += row[(threadIdx.x + i) & 63];      // rotated start: lanes hit distinct banks
+        unsigned long long *dst = (G.mode == 0 ? counts : G.local) + (long long)j * 256 + threadIdx.x;
+        if (c) asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" :: "l"(dst), "l"(c) : "memory");
+    }
+    if (G.mode != 0) group_finish_column(G, j, 256, P.k, chunks_per_col, smem);
 }
 
 // ---------------------------------------------------------------------------------------------

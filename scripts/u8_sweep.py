@@ -47,7 +47,7 @@ def child(mode: int):
 
 
 def main():
-    modes = [int(a) for a in sys.argv[1:]] or [4, 5, 6, 7, 8, 9]
+    modes = [int(a) for a in sys.argv[1:]] or [4, 5, 6, 7, 8, 9, 10, 11]
     allres, ref = [], {}
     for mode in modes:
         out = subprocess.run([sys.executable, __file__, "--child", str(mode)], capture_output=True, text=True)
