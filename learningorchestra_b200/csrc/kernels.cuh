@@ -778,7 +778,7 @@ k_project_cast_hist_tma(const char *__restrict__ in_base, long long in_pitch,
 //   6: like 5 with the powers of two passed as kernel DATA so the shift-and-adds stay IMAD / IMAD.HI on the FMA
 //      pipe and only the masks and the final 1 << n are ALU-pipe work
 #ifndef LO_U8_MODE_DEFAULT
-#define LO_U8_MODE_DEFAULT 7
+#define LO_U8_MODE_DEFAULT 11
 #endif
 
 // two increments with overlapped latencies (one compare instead of bump4's six)

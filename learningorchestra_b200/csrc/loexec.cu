@@ -374,7 +374,8 @@ int hist_u8_impl(lo_ctx *ctx, const lo_table *in, const int32_t *col_idx, int32_
         else if (mode == 5) LO_U8_LAUNCH(true, 5);
         else if (mode == 6) LO_U8_LAUNCH(true, 6);
         else if (mode == 10) LO_U8_LAUNCH(true, 10);
-        else                LO_U8_LAUNCH(true, 7);
+        else if (mode == 7) LO_U8_LAUNCH(true, 7);
+        else                return fail(LO_ERR_INVALID, "unknown LOEXEC_U8_MODE %d", mode);
 #undef LO_U8_LAUNCH
         LO_CUDA(cudaGetLastError());
         ctx->launches.fetch_add(1, std::memory_order_relaxed);
