@@ -1237,6 +1237,8 @@ constexpr int kU8LThreads   = 512;
 constexpr int kU8LSmemBytes = 256 * 64 * 4;                       // 64 KiB
 constexpr int kU8LRoundRows = kU8LThreads * 4 * kU8VecBytes;      // 32 768 rows per loop iteration (4 vectors per thread)
 
+// VAR bit 0: the increment is an opaque register (ATOMS.ADD) instead of the literal 1 (ptxas picks ATOMS.POPC.INC)
+template <int VAR>
 __global__ void __launch_bounds__(kU8LThreads, 3)
 k_hist_u8_cols_lanes(const uint8_t *__restrict__ in_base, long long in_pitch, long long nrows,
                      unsigned chunks_per_col, long long chunk_rows, unsigned long long *__restrict__ counts,
@@ -1250,15 +1252,18 @@ k_hist_u8_cols_lanes(const uint8_t *__restrict__ in_base, long long in_pitch, lo
     const uint8_t *in    = in_base + (long long)P.col[j] * in_pitch + r0;
     if ((uint32_t)__cvta_generic_to_shared(smem) != LO_SMEM_WINDOW_BASE) __trap();     // immediate offset of the atomics
     const uint32_t slot4 = 4u * ((threadIdx.x & 31u) + 32u * ((threadIdx.x >> 5) & 1u));
-    const uint32_t one = 1u;
+    uint32_t one = 1u;
+    if (VAR & 1) one = P.p8 >> 8;                    // a kernel parameter: ptxas cannot fold it into POPC.INC
     const uint8_t *src = in + (long long)threadIdx.x * kU8VecBytes;
+    constexpr long long kStride = (long long)kU8LThreads * kU8VecBytes;        // bytes between a thread's vectors
 
-    uint4 v[4];
-    const bool have_round = n >= kU8LRoundRows;
-    if (have_round) {
+    const long long rounds = n / kU8LRoundRows;
+    uint4 a[4], b[4];                                   // two register sets: one counted while the other is in flight
+    auto load_round = [&](uint4 (&d)[4], long long r) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = ldg128_stream(src + (long long)u * kU8LThreads * kU8VecBytes);
-    }
+        for (int u = 0; u < 4; ++u) d[u] = ldg128_stream(src + r * kU8LRoundRows + u * kStride);
+    };
+    if (rounds > 0) load_round(a, 0);
     {   // clear the counters (overlaps the first loads' DRAM latency)
         uint4 *p = reinterpret_cast<uint4 *>(smem);
         for (int i = threadIdx.x; i < kU8LSmemBytes / 16; i += kU8LThreads) p[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -1274,36 +1279,44 @@ k_hist_u8_cols_lanes(const uint8_t *__restrict__ in_base, long long in_pitch, lo
             atoms_add_base(__byte_perm(w[q], slot4, 0x6534u), one);
         }
     };
-    long long done = 0;
+    auto count_round = [&](const uint4 (&c)[4]) {
+        // a warp whose 2 KiB are one value (constant columns: borders, flags, padding) issues one atomic per lane;
+        // two compares reject mixed data before the full test is paid
+        const uint32_t splat = __byte_perm(c[0].x, 0, 0x0000);
+        if (__all_sync(0xffffffffu, (c[0].x == splat) & (c[3].w == splat))) {
+            uint32_t diff = 0u;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) diff |= (c[u].x ^ splat) | (c[u].y ^ splat) | (c[u].z ^ splat) | (c[u].w ^ splat);
+            if (__all_sync(0xffffffffu, diff == 0u)) {
+                atoms_add_base(((splat & 0xFFu) << 8) | slot4, 64u);
+                return;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) count_vec(c[u]);
+    };
+    long long r = 0;
 #pragma unroll 1
-    for (; done + kU8LRoundRows <= n; done += kU8LRoundRows) {
-        uint4 cur[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) cur[u] = v[u];
-        if (done + 2 * (long long)kU8LRoundRows <= n) {            // next round's loads in flight while this one is counted
-#pragma unroll
-            for (int u = 0; u < 4; ++u) v[u] = ldg128_stream(src + done + kU8LRoundRows + (long long)u * kU8LThreads * kU8VecBytes);
-        }
-        const uint32_t splat = __byte_perm(cur[0].x, 0, 0x0000);
-        uint32_t diff = 0u;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) diff |= (cur[u].x ^ splat) | (cur[u].y ^ splat) | (cur[u].z ^ splat) | (cur[u].w ^ splat);
-        if (__all_sync(0xffffffffu, diff == 0u)) {                 // run of one value (constant columns): one atomic for 64 bytes
-            atoms_add_base(((cur[0].x & 0xFFu) << 8) | slot4, 64u);
-        } else {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) count_vec(cur[u]);
-        }
+    for (; r + 2 <= rounds; r += 2) {
+        load_round(b, r + 1);
+        count_round(a);
+        if (r + 2 < rounds) load_round(a, r + 2);
+        count_round(b);
     }
-    // rest of the chunk: whole vectors, then single bytes
-#pragma unroll 1
-    for (long long e = done + (long long)threadIdx.x * kU8VecBytes; e < n; e += (long long)kU8LThreads * kU8VecBytes) {
-        if (e + kU8VecBytes <= n) {
-            count_vec(ldg128_stream(in + e));
-        } else {
-#pragma unroll 1
-            for (long long q = e; q < n; ++q) atoms_add_base((ldg8_stream(in + q) << 8) | slot4, one);
+    if (r < rounds) count_round(a);
+    {   // rest of the chunk (< one round): every whole vector requested before the first is counted, then single bytes
+        const long long base = rounds * kU8LRoundRows;
+        bool have[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            have[u] = base + (long long)threadIdx.x * kU8VecBytes + u * kStride + kU8VecBytes <= n;
+            if (have[u]) a[u] = ldg128_stream(src + base + u * kStride);
         }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (have[u]) count_vec(a[u]);
+        const long long q = base + ((n - base) / kU8VecBytes) * kU8VecBytes + threadIdx.x;
+        if (q < n) atoms_add_base((ldg8_stream(in + q) << 8) | slot4, one);
     }
     __syncthreads();
     if (G.mode != 0) group_wait_generation(G);

@@ -190,7 +190,8 @@ int configure_kernels() {
     LO_TRY(allow_smem(lo::k_hist_u8_cols<true, 6>));
     LO_TRY(allow_smem(lo::k_hist_u8_cols<true, 7>));
     LO_TRY(allow_smem(lo::k_hist_u8_cols<true, 10>));
-    LO_CUDA(cudaFuncSetAttribute(lo::k_hist_u8_cols_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize, lo::kU8LSmemBytes));
+    LO_CUDA(cudaFuncSetAttribute(lo::k_hist_u8_cols_lanes<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, lo::kU8LSmemBytes));
+    LO_CUDA(cudaFuncSetAttribute(lo::k_hist_u8_cols_lanes<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lo::kU8LSmemBytes));
     LO_TRY(allow_smem(lo::k_hist_u8_cols_wide<2>));
     LO_TRY(allow_smem(lo::k_hist_u8_cols_wide<4>));
     LO_TRY(allow_smem(lo::k_hist_u8_cols<false, 4>));
@@ -337,13 +338,13 @@ int hist_u8_impl(lo_ctx *ctx, const lo_table *in, const int32_t *col_idx, int32_
     int mode = LO_U8_MODE_DEFAULT;
     if (const char *e = getenv("LOEXEC_U8_MODE")) mode = atoi(e);       // measurement knob (scripts/u8_sweep.py)
     const bool wide = aligned && (mode == 8 || mode == 9);
-    const bool lanes = aligned && mode == 11;
+    const bool lanes = aligned && (mode == 11 || mode == 12);
     int64_t tile_rows = !wide ? lo::kU8TileRows : mode == 8 ? lo::kU8WTileRows2 : lo::kU8WTileRows4;
     if (lanes) {
-        // chunk of a column per CTA: long enough to amortise the 64 KiB clear + fold, short enough for >= ~8 waves of
-        // CTAs (3 resident per SM); a multiple of the 32 Ki-row loop round
+        // chunk of a column per CTA, a multiple of the 32 Ki-row round: long chunks amortise the 64 KiB clear + fold
+        // (8 rounds measured best on 1 M+ row tables, one chunk per column on 125 K-row shards: r02_u8_sweep_chunks.json)
         const int64_t slots = (int64_t)ctx->sm_count * 3;
-        int64_t want = (in->nrows * (int64_t)std::min<int32_t>(k, lo::kMaxColsU8)) / (8 * slots);
+        int64_t want = (in->nrows * (int64_t)std::min<int32_t>(k, lo::kMaxColsU8)) / slots;
         want = std::max<int64_t>(lo::kU8LRoundRows, std::min<int64_t>(want, 8 * (int64_t)lo::kU8LRoundRows));
         if (const char *e = getenv("LOEXEC_U8_CHUNK_ROUNDS")) want = std::max<int64_t>(1, atoll(e)) * lo::kU8LRoundRows;
         tile_rows = (want / lo::kU8LRoundRows) * lo::kU8LRoundRows;
@@ -365,7 +366,9 @@ int hist_u8_impl(lo_ctx *ctx, const lo_table *in, const int32_t *col_idx, int32_
         if (!aligned)       LO_U8_LAUNCH(false, 4);
         else if (mode == 8) LO_CUDA(launch_kernel(lo::k_hist_u8_cols_wide<2>, (unsigned)blocks, 512u, (size_t)lo::kHistSmemBytes, s,
                                                   G.overlap != 0, ib, ip, nr, tiles_per_col, cnt, P, G));
-        else if (lanes)     LO_CUDA(launch_kernel(lo::k_hist_u8_cols_lanes, (unsigned)blocks, (unsigned)lo::kU8LThreads, (size_t)lo::kU8LSmemBytes, s,
+        else if (mode == 11) LO_CUDA(launch_kernel(lo::k_hist_u8_cols_lanes<0>, (unsigned)blocks, (unsigned)lo::kU8LThreads, (size_t)lo::kU8LSmemBytes, s,
+                                                  G.overlap != 0, ib, ip, nr, tiles_per_col, (long long)tile_rows, cnt, P, G));
+        else if (mode == 12) LO_CUDA(launch_kernel(lo::k_hist_u8_cols_lanes<1>, (unsigned)blocks, (unsigned)lo::kU8LThreads, (size_t)lo::kU8LSmemBytes, s,
                                                   G.overlap != 0, ib, ip, nr, tiles_per_col, (long long)tile_rows, cnt, P, G));
         else if (mode == 9) LO_CUDA(launch_kernel(lo::k_hist_u8_cols_wide<4>, (unsigned)blocks, 1024u, (size_t)lo::kHistSmemBytes, s,
                                                   G.overlap != 0, ib, ip, nr, tiles_per_col, cnt, P, G));

@@ -27,14 +27,18 @@ def child(mode: int):
     eng = Engine(0)
     stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
     tables = {}
-    tables["mnist_1Mx784"] = (eng.table("u8", 1_000_000, 784).fill_synthetic(3, 20260921, stream=stream), 784)
-    tables["mnist_8Mx784"] = (eng.table("u8", 8_000_000, 784).fill_synthetic(3, 20260921, stream=stream), 784)
-    rng = np.random.default_rng(3)
-    dense = eng.table("u8", 4_000_000, 128)
-    blk = rng.integers(0, 256, 4_000_000, dtype=np.uint8)
-    for c in range(128):
-        dense.upload(c, np.roll(blk, c * 977))
-    tables["dense_random_4Mx128"] = (dense, 128)
+    only = os.environ.get("U8_SWEEP_TABLES", "")          # substring filter (for one-table ncu captures)
+    if only in "mnist_1Mx784":
+        tables["mnist_1Mx784"] = (eng.table("u8", 1_000_000, 784).fill_synthetic(3, 20260921, stream=stream), 784)
+    if only in "mnist_8Mx784":
+        tables["mnist_8Mx784"] = (eng.table("u8", 8_000_000, 784).fill_synthetic(3, 20260921, stream=stream), 784)
+    if only in "dense_random_4Mx128":
+        rng = np.random.default_rng(3)
+        dense = eng.table("u8", 4_000_000, 128)
+        blk = rng.integers(0, 256, 4_000_000, dtype=np.uint8)
+        for c in range(128):
+            dense.upload(c, np.roll(blk, c * 977))
+        tables["dense_random_4Mx128"] = (dense, 128)
     res = []
     for name, (t, k) in tables.items():
         c = eng.counts(k, 256)
@@ -47,7 +51,7 @@ def child(mode: int):
 
 
 def main():
-    modes = [int(a) for a in sys.argv[1:]] or [4, 5, 6, 7, 8, 9, 10, 11]
+    modes = [int(a) for a in sys.argv[1:]] or [4, 5, 6, 7, 8, 9, 10, 11, 12]
     allres, ref = [], {}
     for mode in modes:
         out = subprocess.run([sys.executable, __file__, "--child", str(mode)], capture_output=True, text=True)
