@@ -55,7 +55,7 @@ WORKLOADS = {
              "kernel": "lo::k_project_cast_hist<1,true,true,true>"},
     "s10": {"rows": 10_000_000, "cols": 16, "dtype": "f64->f32", "bytes_per_elem": 12.0,
             "kernel": "lo::k_project_cast_hist<1,false,true,false>"},
-    "m": {"rows": 1_000_000, "cols": 784, "dtype": "u8", "bytes_per_elem": 1.0, "kernel": "lo::k_hist_u8_cols_lanes<0>"},
+    "m": {"rows": 1_000_000, "cols": 784, "dtype": "u8", "bytes_per_elem": 1.0, "kernel": "lo::k_hist_u8_cols_lanes<2>"},
 }
 
 

@@ -772,7 +772,8 @@ k_project_cast_hist_tma(const char *__restrict__ in_base, long long in_pitch,
 //   7: the counter word's whole shared-memory address from ONE PRMT (thread bits pre-merged into the row bytes), the
 //      field value from one wrap-mode funnel shift, the run test once per 80-byte batch: ~4.7 instead of ~6.3
 //      instructions per byte
-//   11: k_hist_u8_cols_lanes — 32-bit counters in 64 lane slots shared by all warps of the CTA: one PRMT + one ATOMS per byte
+//   11: k_hist_u8_cols_lanes — 32-bit counters in 64 lane slots shared by all warps of the CTA: one PRMT + one ATOMS per
+//       byte (shipped; 12-14: its measurement variants)
 //   8 / 9: k_hist_u8_cols_wide<2 / 4> — mode 7's arithmetic with 512 / 1024 threads per CTA, two / four threads per
 //      private histogram (48 / 64 warps per SM)
 //   6: like 5 with the powers of two passed as kernel DATA so the shift-and-adds stay IMAD / IMAD.HI on the FMA
@@ -1238,6 +1239,9 @@ constexpr int kU8LSmemBytes = 256 * 64 * 4;                       // 64 KiB
 constexpr int kU8LRoundRows = kU8LThreads * 4 * kU8VecBytes;      // 32 768 rows per loop iteration (4 vectors per thread)
 
 // VAR bit 0: the increment is an opaque register (ATOMS.ADD) instead of the literal 1 (ptxas picks ATOMS.POPC.INC)
+// VAR bit 1: one register set copied per round instead of two alternating sets;  bit 2: no two-compare quick reject
+// before the run test.  LOEXEC_U8_MODE 11 = VAR 2 (shipped: the copy form is 2-3 % faster than alternating sets,
+// profiles/r02_u8_sweep_lanes_loop_forms.json), 12 = VAR 3, 13 = VAR 0, 14 = VAR 6
 template <int VAR>
 __global__ void __launch_bounds__(kU8LThreads, 3)
 k_hist_u8_cols_lanes(const uint8_t *__restrict__ in_base, long long in_pitch, long long nrows,
@@ -1258,7 +1262,7 @@ k_hist_u8_cols_lanes(const uint8_t *__restrict__ in_base, long long in_pitch, lo
     constexpr long long kStride = (long long)kU8LThreads * kU8VecBytes;        // bytes between a thread's vectors
 
     const long long rounds = n / kU8LRoundRows;
-    uint4 a[4], b[4];                                   // two register sets: one counted while the other is in flight
+    uint4 a[4], b[4];                                   // one set in flight while the other is counted
     auto load_round = [&](uint4 (&d)[4], long long r) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) d[u] = ldg128_stream(src + r * kU8LRoundRows + u * kStride);
@@ -1283,7 +1287,7 @@ k_hist_u8_cols_lanes(const uint8_t *__restrict__ in_base, long long in_pitch, lo
         // a warp whose 2 KiB are one value (constant columns: borders, flags, padding) issues one atomic per lane;
         // two compares reject mixed data before the full test is paid
         const uint32_t splat = __byte_perm(c[0].x, 0, 0x0000);
-        if (__all_sync(0xffffffffu, (c[0].x == splat) & (c[3].w == splat))) {
+        if ((VAR & 4) || __all_sync(0xffffffffu, (c[0].x == splat) & (c[3].w == splat))) {
             uint32_t diff = 0u;
 #pragma unroll
             for (int u = 0; u < 4; ++u) diff |= (c[u].x ^ splat) | (c[u].y ^ splat) | (c[u].z ^ splat) | (c[u].w ^ splat);
@@ -1296,14 +1300,24 @@ k_hist_u8_cols_lanes(const uint8_t *__restrict__ in_base, long long in_pitch, lo
         for (int u = 0; u < 4; ++u) count_vec(c[u]);
     };
     long long r = 0;
+    if (VAR & 2) {                                       // loads land in a[], a copy is counted
 #pragma unroll 1
-    for (; r + 2 <= rounds; r += 2) {
-        load_round(b, r + 1);
-        count_round(a);
-        if (r + 2 < rounds) load_round(a, r + 2);
-        count_round(b);
+        for (; r < rounds; ++r) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) b[u] = a[u];
+            if (r + 1 < rounds) load_round(a, r + 1);
+            count_round(b);
+        }
+    } else {
+#pragma unroll 1
+        for (; r + 2 <= rounds; r += 2) {
+            load_round(b, r + 1);
+            count_round(a);
+            if (r + 2 < rounds) load_round(a, r + 2);
+            count_round(b);
+        }
+        if (r < rounds) count_round(a);
     }
-    if (r < rounds) count_round(a);
     {   // rest of the chunk (< one round): every whole vector requested before the first is counted, then single bytes
         const long long base = rounds * kU8LRoundRows;
         bool have[4];

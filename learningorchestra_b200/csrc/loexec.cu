@@ -191,7 +191,9 @@ int configure_kernels() {
     LO_TRY(allow_smem(lo::k_hist_u8_cols<true, 7>));
     LO_TRY(allow_smem(lo::k_hist_u8_cols<true, 10>));
     LO_CUDA(cudaFuncSetAttribute(lo::k_hist_u8_cols_lanes<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, lo::kU8LSmemBytes));
-    LO_CUDA(cudaFuncSetAttribute(lo::k_hist_u8_cols_lanes<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lo::kU8LSmemBytes));
+    LO_CUDA(cudaFuncSetAttribute(lo::k_hist_u8_cols_lanes<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, lo::kU8LSmemBytes));
+    LO_CUDA(cudaFuncSetAttribute(lo::k_hist_u8_cols_lanes<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lo::kU8LSmemBytes));
+    LO_CUDA(cudaFuncSetAttribute(lo::k_hist_u8_cols_lanes<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, lo::kU8LSmemBytes));
     LO_TRY(allow_smem(lo::k_hist_u8_cols_wide<2>));
     LO_TRY(allow_smem(lo::k_hist_u8_cols_wide<4>));
     LO_TRY(allow_smem(lo::k_hist_u8_cols<false, 4>));
@@ -338,7 +340,7 @@ int hist_u8_impl(lo_ctx *ctx, const lo_table *in, const int32_t *col_idx, int32_
     int mode = LO_U8_MODE_DEFAULT;
     if (const char *e = getenv("LOEXEC_U8_MODE")) mode = atoi(e);       // measurement knob (scripts/u8_sweep.py)
     const bool wide = aligned && (mode == 8 || mode == 9);
-    const bool lanes = aligned && (mode == 11 || mode == 12);
+    const bool lanes = aligned && mode >= 11 && mode <= 14;
     int64_t tile_rows = !wide ? lo::kU8TileRows : mode == 8 ? lo::kU8WTileRows2 : lo::kU8WTileRows4;
     if (lanes) {
         // chunk of a column per CTA, a multiple of the 32 Ki-row round: long chunks amortise the 64 KiB clear + fold
@@ -366,9 +368,13 @@ int hist_u8_impl(lo_ctx *ctx, const lo_table *in, const int32_t *col_idx, int32_
         if (!aligned)       LO_U8_LAUNCH(false, 4);
         else if (mode == 8) LO_CUDA(launch_kernel(lo::k_hist_u8_cols_wide<2>, (unsigned)blocks, 512u, (size_t)lo::kHistSmemBytes, s,
                                                   G.overlap != 0, ib, ip, nr, tiles_per_col, cnt, P, G));
-        else if (mode == 11) LO_CUDA(launch_kernel(lo::k_hist_u8_cols_lanes<0>, (unsigned)blocks, (unsigned)lo::kU8LThreads, (size_t)lo::kU8LSmemBytes, s,
+        else if (mode == 11) LO_CUDA(launch_kernel(lo::k_hist_u8_cols_lanes<2>, (unsigned)blocks, (unsigned)lo::kU8LThreads, (size_t)lo::kU8LSmemBytes, s,
                                                   G.overlap != 0, ib, ip, nr, tiles_per_col, (long long)tile_rows, cnt, P, G));
-        else if (mode == 12) LO_CUDA(launch_kernel(lo::k_hist_u8_cols_lanes<1>, (unsigned)blocks, (unsigned)lo::kU8LThreads, (size_t)lo::kU8LSmemBytes, s,
+        else if (mode == 12) LO_CUDA(launch_kernel(lo::k_hist_u8_cols_lanes<3>, (unsigned)blocks, (unsigned)lo::kU8LThreads, (size_t)lo::kU8LSmemBytes, s,
+                                                  G.overlap != 0, ib, ip, nr, tiles_per_col, (long long)tile_rows, cnt, P, G));
+        else if (mode == 13) LO_CUDA(launch_kernel(lo::k_hist_u8_cols_lanes<0>, (unsigned)blocks, (unsigned)lo::kU8LThreads, (size_t)lo::kU8LSmemBytes, s,
+                                                  G.overlap != 0, ib, ip, nr, tiles_per_col, (long long)tile_rows, cnt, P, G));
+        else if (mode == 14) LO_CUDA(launch_kernel(lo::k_hist_u8_cols_lanes<6>, (unsigned)blocks, (unsigned)lo::kU8LThreads, (size_t)lo::kU8LSmemBytes, s,
                                                   G.overlap != 0, ib, ip, nr, tiles_per_col, (long long)tile_rows, cnt, P, G));
         else if (mode == 9) LO_CUDA(launch_kernel(lo::k_hist_u8_cols_wide<4>, (unsigned)blocks, 1024u, (size_t)lo::kHistSmemBytes, s,
                                                   G.overlap != 0, ib, ip, nr, tiles_per_col, cnt, P, G));

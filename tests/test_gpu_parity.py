@@ -147,7 +147,7 @@ def test_hist_u8_all_values_and_constant(engine):
     t.free()
 
 
-@pytest.mark.parametrize("mode", ["2", "4", "5", "6", "7", "8", "9", "10", "11", "12"])
+@pytest.mark.parametrize("mode", ["2", "4", "5", "6", "7", "8", "9", "10", "11", "12", "13", "14"])
 def test_hist_u8_every_kernel_variant(engine, monkeypatch, mode):
     """Every selectable form of the byte-histogram kernel (LOEXEC_U8_MODE; 8 = the 512-thread shared-histogram kernel
     with its own tile size) gives the oracle's counts: ragged sizes, full tiles, constant columns, every byte value."""
