@@ -1,4 +1,5 @@
-"""Summarise an .ncu-rep (read here, no GPU needed) into profiles/<tag>_summary.{json,md} and update profiles/traffic.json."""
+"""Summarise an .ncu-rep (read here, no GPU needed) into profiles/<tag>_summary.{json,md} and, when a third argument names the bench key
+(k_project_cast_hist_bytes_per_launch / k_hist_u8_cols_bytes_per_launch), record the launch's DRAM bytes in profiles/traffic.json."""
 import csv, io, json, subprocess, sys
 from pathlib import Path
 
@@ -39,11 +40,12 @@ def main(rep, tag, kernel_key):
     r = summ[0]
     rd = scale(r["dram__bytes_read.sum"]["value"], r["dram__bytes_read.sum"]["unit"])
     wr = scale(r["dram__bytes_write.sum"]["value"], r["dram__bytes_write.sum"]["unit"])
-    tr_path = P / "traffic.json"
-    tr = json.loads(tr_path.read_text()) if tr_path.exists() else {}
-    tr[kernel_key] = rd + wr
-    tr[kernel_key + "_source"] = f"profiles/{tag}_summary.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, one launch)"
-    tr_path.write_text(json.dumps(tr, indent=1))
+    if kernel_key:                       # only when the caller names the bench key this capture is the full-size launch of
+        tr_path = P / "traffic.json"
+        tr = json.loads(tr_path.read_text()) if tr_path.exists() else {}
+        tr[kernel_key] = rd + wr
+        tr[kernel_key + "_source"] = f"profiles/{tag}_summary.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, one launch)"
+        tr_path.write_text(json.dumps(tr, indent=1))
     lines = [f"# ncu --set full summary: {tag}", "", f"kernel: `{r['kernel']}`  grid {r['grid']} block {r['block']}", ""]
     for k in KEYS:
         if k in r:
@@ -55,4 +57,4 @@ def main(rep, tag, kernel_key):
     print("\n".join(lines))
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else "k_project_cast_hist_bytes_per_launch")
+    main(sys.argv[1], sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else None)
