@@ -666,8 +666,10 @@ def run_gpu(args) -> int:
                "rows_per_step": int(float(rr[0])), "steps": e2e_steps, "launches": e2e_launches,
                "h2d_GBs_slowest_rank": float(mn[0]), "numa": {"node": numa[0], "cpus": numa[1]} if numa else None,
                "counts_match_golden": e2e_parity,
-               "api": "ShardedEngine.project_cast_hist_host -> lo_group_project_cast_hist_host (pinned host buffers, "
-                      "chunked H2D / kernel / D2H on three streams per GPU, counts merged over the group)"}
+               "api": ("ShardedEngine.hist_u8_cols_host -> lo_group_hist_u8_cols_host" if w == "m" else
+                       "ShardedEngine.project_cast_hist_host -> lo_group_project_cast_hist_host")
+                      + " (pinned host buffers, chunked H2D / kernel / D2H on three streams per GPU, equally strided "
+                        "columns as one 2-D copy per chunk, counts merged over the group)"}
         os.sched_setaffinity(0, saved_affinity)
 
     rc = 0

@@ -892,6 +892,32 @@ int lo_counts_download(lo_ctx *ctx, const uint64_t *counts_dev, int64_t n, uint6
 
 namespace {
 
+// One chunk of k host columns <-> k staging slabs.  Host columns that sit at a constant stride (one 2-D array, the
+// usual case: a numpy matrix, an Arrow table's buffers from one allocation) go as ONE strided 2-D copy per run instead
+// of one copy per column: 784 byte columns x 5 chunks were 3 920 submissions of 192 KiB each (27 GB/s); a run is one.
+int copy_cols(char *dev_base, int64_t dev_pitch, const void *const *host_cols, int64_t host_off, size_t bytes, int32_t k,
+              bool to_device, cudaStream_t s) {
+    for (int32_t j = 0; j < k;) {
+        int32_t e = j + 1;
+        const ptrdiff_t stride = (e < k) ? (const char *)host_cols[e] - (const char *)host_cols[j] : 0;
+        if (stride >= (ptrdiff_t)bytes && stride <= (ptrdiff_t)0x7fffffff)
+            while (e < k && (const char *)host_cols[e] - (const char *)host_cols[e - 1] == stride) ++e;
+        else
+            e = j + 1;
+        char *d = dev_base + (int64_t)j * dev_pitch;
+        char *h = (char *)host_cols[j] + host_off;
+        if (e - j >= 2) {
+            if (to_device) LO_CUDA(cudaMemcpy2DAsync(d, (size_t)dev_pitch, h, (size_t)stride, bytes, (size_t)(e - j), cudaMemcpyHostToDevice, s));
+            else           LO_CUDA(cudaMemcpy2DAsync(h, (size_t)stride, d, (size_t)dev_pitch, bytes, (size_t)(e - j), cudaMemcpyDeviceToHost, s));
+        } else {
+            if (to_device) LO_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, s));
+            else           LO_CUDA(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, s));
+        }
+        j = e;
+    }
+    return LO_OK;
+}
+
 template <typename Launch>
 int host_pipeline(lo_ctx *ctx, const void *const *in_cols, int in_dtype, int64_t nrows, int32_t k,
                   void *const *out_cols, int out_dtype, int64_t tile_rows, size_t ncounts, uint64_t *counts_host,
@@ -917,10 +943,7 @@ int host_pipeline(lo_ctx *ctx, const void *const *in_cols, int in_dtype, int64_t
                 const int slot = (int)(c % kSlots);
                 const int64_t r0 = c * crows, n = std::min(crows, nrows - r0);
                 if (c >= kSlots) LO_CUDA(cudaStreamWaitEvent(st->h2d, st->ev_k[slot], 0));
-                for (int j = 0; j < k; ++j)
-                    LO_CUDA(cudaMemcpyAsync(st->in[slot] + (int64_t)j * in_pitch,
-                                            (const char *)in_cols[j] + r0 * (int64_t)ies, (size_t)n * ies,
-                                            cudaMemcpyHostToDevice, st->h2d));
+                LO_TRY(copy_cols(st->in[slot], in_pitch, in_cols, r0 * (int64_t)ies, (size_t)n * ies, k, true, st->h2d));
                 h2d += (double)n * ies * k;
                 LO_CUDA(cudaEventRecord(st->ev_h2d[slot], st->h2d));
                 LO_CUDA(cudaStreamWaitEvent(st->compute, st->ev_h2d[slot], 0));
@@ -931,10 +954,8 @@ int host_pipeline(lo_ctx *ctx, const void *const *in_cols, int in_dtype, int64_t
                 LO_CUDA(cudaEventRecord(st->ev_k[slot], st->compute));
                 if (out_cols) {
                     LO_CUDA(cudaStreamWaitEvent(st->d2h, st->ev_k[slot], 0));
-                    for (int j = 0; j < k; ++j)
-                        LO_CUDA(cudaMemcpyAsync((char *)out_cols[j] + r0 * (int64_t)oes,
-                                                st->out[slot] + (int64_t)j * out_pitch, (size_t)n * oes,
-                                                cudaMemcpyDeviceToHost, st->d2h));
+                    LO_TRY(copy_cols(st->out[slot], out_pitch, (const void *const *)out_cols, r0 * (int64_t)oes, (size_t)n * oes, k,
+                                     false, st->d2h));
                     d2h += (double)n * oes * k;
                     LO_CUDA(cudaEventRecord(st->ev_d2h[slot], st->d2h));
                 }

@@ -207,6 +207,38 @@ def test_host_buffer_entry_points(engine):
     np.testing.assert_array_equal(c8, bn.hist_u8_cols(tb, range(30)))
 
 
+def test_host_columns_in_every_memory_arrangement(engine):
+    """The host pipeline moves runs of equally strided columns as one 2-D copy and everything else column by column:
+    rows of one matrix (in order, every other row, reversed), separately allocated arrays and a mix must all give the
+    oracle's answer, inputs and outputs alike."""
+    nrows, k = 700_003, 8
+    table = bn.synth_table_f64(1, SEED + 21, k, 0, nrows)
+    lo = np.full(k, -1000, np.float32); hi = np.full(k, 1000, np.float32)
+    exp_out, exp_counts = bn.project_cast_hist(table, range(k), 64, lo, hi)
+    wide = np.zeros((2 * k, nrows + 5), dtype=np.float64)          # row stride != nrows * 8; every other row used
+    wide[::2, :nrows] = table
+    out_mat = np.empty((k, nrows), dtype=np.float32)
+    arrangements = {
+        "matrix rows": ([table[j] for j in range(k)], [out_mat[j] for j in range(k)]),
+        "every other row of a wider matrix": ([wide[2 * j, :nrows] for j in range(k)], [np.empty(nrows, np.float32) for _ in range(k)]),
+        "separate arrays": ([table[j].copy() for j in range(k)], [out_mat[k - 1 - j] for j in range(k)]),      # outputs reversed
+        "mixed": ([table[0], table[1], table[2].copy(), table[3], wide[8, :nrows], wide[10, :nrows], table[6], table[7].copy()],
+                  [np.empty(nrows, np.float32) if j % 3 == 0 else out_mat[j] for j in range(k)]),
+    }
+    for name, (cols, outs) in arrangements.items():
+        counts, timing = engine.project_cast_hist_host(cols, 64, lo, hi, out=outs)
+        np.testing.assert_array_equal(counts, exp_counts, err_msg=name)
+        for j in range(k):
+            np.testing.assert_array_equal(_bits(outs[j]), _bits(exp_out[j]), err_msg=f"{name}, column {j}")
+        assert timing["h2d_bytes"] == nrows * k * 8
+    rev, _ = engine.project_cast_hist_host([table[k - 1 - j] for j in range(k)], 64, lo, hi)       # negative stride
+    np.testing.assert_array_equal(rev, exp_counts[::-1])
+    tb = bn.synth_table_u8(SEED, 40, 0, 300_001)                    # bytes: 40 columns of one matrix, then scattered
+    want = bn.hist_u8_cols(tb, range(40))
+    np.testing.assert_array_equal(engine.hist_u8_cols_host([tb[j] for j in range(40)])[0], want)
+    np.testing.assert_array_equal(engine.hist_u8_cols_host([tb[j].copy() if j % 5 == 0 else tb[j] for j in range(40)])[0], want)
+
+
 def test_error_reporting(engine):
     from learningorchestra_b200._native import LoexecError, LO_ERR_INVALID
     t = engine.table("f64", 100, 2)
