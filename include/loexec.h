@@ -65,7 +65,9 @@ extern "C" {
 #define LO_SYNTH_CONSTCOL  2  /* EDGES + column 0 constant (contention worst case)           */
 #define LO_SYNTH_MNIST_U8  3  /* u8: 28x28 image columns, border 0, ~80 % zeros overall      */
 
-#define LO_MAX_BINS 256       /* per-thread byte-counter histograms hold <= 256 bins          */
+#define LO_MAX_BINS 65536     /* bins per column of a binned histogram                         */
+#define LO_TILE_BINS 256      /* up to here the fused tile kernel's per-thread byte counters;  */
+                              /* above: the chunk kernel's 32-bit shared / L2 counters         */
 
 typedef struct lo_ctx   lo_ctx;    /* one per (process, device) */
 typedef struct lo_table lo_table;  /* columnar table: ncols slabs of nrows elements, one dtype */
@@ -74,7 +76,9 @@ typedef struct lo_table lo_table;  /* columnar table: ncols slabs of nrows eleme
  *   for projected column j with range [lo[j], hi[j]] (fp32) and nbins bins, over the
  *   CAST fp32 value x:  skip NaN and x outside [lo,hi];  w = (hi-lo)/nbins (fp32 RN);
  *   i = (int)((x-lo)/w) (fp32 RN sub, fp32 RN div, truncate);  i = min(i, nbins-1).
- *   lo/hi are HOST arrays of k floats.  Counts are uint64, layout [k][nbins]. */
+ *   lo/hi are HOST arrays of k floats.  Counts are uint64, layout [k][nbins].
+ *   nbins <= LO_TILE_BINS runs the fused tile kernel, larger nbins the chunk kernel (same arithmetic and results;
+ *   DESIGN.md 3.4.1). */
 typedef struct lo_hist_spec {
     int32_t      nbins;     /* 1..LO_MAX_BINS */
     int32_t      flags;     /* must be 0 */

@@ -25,7 +25,7 @@ LO_ERR_ALIGNMENT = -6
 
 LO_F64, LO_F32, LO_U8, LO_U32 = 1, 2, 3, 4
 LO_SYNTH_UNIFORM, LO_SYNTH_EDGES, LO_SYNTH_CONSTCOL, LO_SYNTH_MNIST_U8 = 0, 1, 2, 3
-LO_MAX_BINS = 256
+LO_MAX_BINS = 65536
 LO_MERGE_AUTO, LO_MERGE_PEER, LO_MERGE_NCCL = 0, 1, 2
 LO_GROUP_BCAST = 1
 LO_GROUP_INDEPENDENT = 2

@@ -593,6 +593,95 @@ k_project_cast_hist(const char *__restrict__ in_base, long long in_pitch,
 }
 
 // ---------------------------------------------------------------------------------------------
+// K1+K2+K3 for histograms wider than the per-thread byte counters hold (256 < nbins <= LO_MAX_BINS): the optional
+// ``bins`` key of the REST request is not capped at 256.  Same projection, cast and binning arithmetic; the counters
+// are 32-bit words in shared memory, nbins x S lane slots (S = the largest power of two <= 32 with nbins * S <= 16 Ki
+// words; slot = lane mod S, so S = 32 is conflict-free and smaller S spreads equal bins of one instruction over S
+// words), one ATOMS per element; up to 56 Ki bins one slot per bin in 224 KiB (one CTA per SM); above that the increments go
+// straight to the count matrix in L2 (RED.64: with that many bins two lanes rarely meet).  A CTA streams a chunk of one projected column and folds once (32-bit
+// counters: chunk_rows < 2^31).  HBM-bound like the 256-bin kernel: 12 B and one shared-memory atomic per element.
+// grid.x = k * chunks_per_col
+// ---------------------------------------------------------------------------------------------
+constexpr int kWBThreads   = 512;
+constexpr int kWBSmemWords = 16384;                                  // 64 KiB: two CTAs per SM
+constexpr int kWBSmemWordsMax = 57344;                               // 224 KiB: one CTA per SM, one slot per bin
+constexpr int kWBRoundRows = kWBThreads * kVec * 2;                  // two 32-byte vectors per thread per loop round
+
+template <int OUT, bool FASTDIV>
+__global__ void __launch_bounds__(kWBThreads, 2)
+k_project_cast_hist_bins(const char *__restrict__ in_base, long long in_pitch, char *__restrict__ out_base, long long out_pitch,
+                         long long nrows, unsigned chunks_per_col, long long chunk_rows, int slots_log2 /* < 0: no smem */,
+                         int aligned, unsigned long long *__restrict__ counts,
+                         const __grid_constant__ ColsF64 P, const __grid_constant__ GroupStep G) {
+    extern __shared__ uint32_t smem[];
+    if (G.overlap) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const unsigned j     = blockIdx.x / chunks_per_col;
+    const unsigned chunk = blockIdx.x - j * chunks_per_col;
+    const long long r0   = (long long)chunk * chunk_rows;
+    const long long n    = min(chunk_rows, nrows - r0);
+    const double *in = reinterpret_cast<const double *>(in_base + (long long)P.col[j] * in_pitch) + r0;
+    float  *out32 = (OUT == 1) ? reinterpret_cast<float *>(out_base + (long long)j * out_pitch) + r0 : nullptr;
+    double *out64 = (OUT == 2) ? reinterpret_cast<double *>(out_base + (long long)j * out_pitch) + r0 : nullptr;
+    const int nb = P.nbins;
+    BinParams B = {P.lo[j], P.hi[j], P.w[j], __frcp_rn(P.w[j]), nb - 1};
+    unsigned long long *dst = (G.mode == 0 ? counts : G.local) + (long long)j * nb;
+    const bool in_smem = slots_log2 >= 0;
+    const int  sl = in_smem ? slots_log2 : 0;
+    const uint32_t slot = threadIdx.x & ((1u << sl) - 1u);
+    if (in_smem) {
+        for (int i = threadIdx.x; i < (nb << sl); i += kWBThreads) smem[i] = 0u;
+        __syncthreads();
+    } else if (G.mode != 0) {
+        group_wait_generation(G);                       // the increments land in G.local as they are issued
+    }
+    auto count = [&](float f) {
+        const int i = bin_index_f32<FASTDIV>(f, B);
+        if (i >= 0) {
+            if (in_smem) atomicAdd(smem + ((uint32_t)i << sl) + slot, 1u);
+            else asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" :: "l"(dst + i), "l"(1ull) : "memory");
+        }
+    };
+    long long done = 0;
+    if (aligned) {
+        const double *src = in + (long long)threadIdx.x * kVec;
+#pragma unroll 1
+        for (; done + kWBRoundRows <= n; done += kWBRoundRows) {
+            double v[2][4];
+            ldg256_stream(src + done, v[0]);
+            ldg256_stream(src + done + (long long)kWBThreads * kVec, v[1]);
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const long long e = done + ((long long)u * kWBThreads + threadIdx.x) * kVec;
+                const float f0 = cast_f64_f32(v[u][0]), f1 = cast_f64_f32(v[u][1]), f2 = cast_f64_f32(v[u][2]), f3 = cast_f64_f32(v[u][3]);
+                if (OUT == 1) stg128_stream(out32 + e, f0, f1, f2, f3);
+                if (OUT == 2) stg256_stream(out64 + e, v[u]);
+                count(f0); count(f1); count(f2); count(f3);
+            }
+        }
+    }
+    // the rest of the chunk (all of it for unaligned slabs): element-wise, lane-contiguous
+#pragma unroll 1
+    for (long long e = done + threadIdx.x; e < n; e += kWBThreads) {
+        const double x = ldg64_stream(in + e);
+        const float  f = cast_f64_f32(x);
+        if (OUT == 1) out32[e] = f;
+        if (OUT == 2) out64[e] = x;
+        count(f);
+    }
+    if (in_smem) {
+        __syncthreads();
+        if (G.mode != 0) group_wait_generation(G);
+        const uint32_t S = 1u << sl;
+        for (int b = threadIdx.x; b < nb; b += kWBThreads) {
+            unsigned long long c = 0;
+            for (uint32_t i = 0; i < S; ++i) c += smem[((uint32_t)b << sl) + ((i + threadIdx.x) & (S - 1u))];   // rotated: no bank conflicts
+            if (c) asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" :: "l"(dst + b), "l"(c) : "memory");
+        }
+    }
+    if (G.mode != 0) group_finish_column(G, j, nb, P.k, chunks_per_col, smem);
+}
+
+// ---------------------------------------------------------------------------------------------
 // K1+K2+K3, TMA form (LOEXEC_TMA=1): the same tile, but the column slab is staged into shared memory by the
 // bulk-copy engine (cp.async.bulk global -> shared, completion on an mbarrier) through a kTmaStages-deep ring
 // driven by one producer thread; the 256 consumer threads read their 32 bytes from the ring instead of

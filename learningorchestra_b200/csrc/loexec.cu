@@ -194,6 +194,12 @@ int configure_kernels() {
     LO_CUDA(cudaFuncSetAttribute(lo::k_hist_u8_cols_lanes<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, lo::kU8LSmemBytes));
     LO_CUDA(cudaFuncSetAttribute(lo::k_hist_u8_cols_lanes<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lo::kU8LSmemBytes));
     LO_CUDA(cudaFuncSetAttribute(lo::k_hist_u8_cols_lanes<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, lo::kU8LSmemBytes));
+    LO_CUDA(cudaFuncSetAttribute(lo::k_project_cast_hist_bins<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lo::kWBSmemWordsMax * 4));
+    LO_CUDA(cudaFuncSetAttribute(lo::k_project_cast_hist_bins<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lo::kWBSmemWordsMax * 4));
+    LO_CUDA(cudaFuncSetAttribute(lo::k_project_cast_hist_bins<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lo::kWBSmemWordsMax * 4));
+    LO_CUDA(cudaFuncSetAttribute(lo::k_project_cast_hist_bins<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lo::kWBSmemWordsMax * 4));
+    LO_CUDA(cudaFuncSetAttribute(lo::k_project_cast_hist_bins<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lo::kWBSmemWordsMax * 4));
+    LO_CUDA(cudaFuncSetAttribute(lo::k_project_cast_hist_bins<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lo::kWBSmemWordsMax * 4));
     LO_TRY(allow_smem(lo::k_hist_u8_cols_wide<2>));
     LO_TRY(allow_smem(lo::k_hist_u8_cols_wide<4>));
     LO_TRY(allow_smem(lo::k_hist_u8_cols<false, 4>));
@@ -273,6 +279,41 @@ int launch_f64(lo_ctx *ctx, const lo_table *in, const lo_table *out, int32_t out
     return LO_OK;
 }
 
+// histograms wider than the byte-counter tile kernel holds (LO_TILE_BINS < nbins <= LO_MAX_BINS): k_project_cast_hist_bins
+template <int OUT>
+int launch_f64_bins(lo_ctx *ctx, const lo_table *in, const lo_table *out, int32_t out_col0,
+                    const lo::ColsF64 &P, unsigned long long *counts, bool aligned, const lo::GroupStep &G, cudaStream_t s) {
+    char *out_base = out ? out->base + (int64_t)out_col0 * out->pitch : nullptr;
+    const long long out_pitch = out ? out->pitch : 0;
+    bool fast = true;
+    for (int j = 0; j < P.k; ++j) fast = fast && fastdiv_ok(P.w[j]);
+    int slots_log2 = -1;                                  // counters in shared memory while one slot per bin fits 224 KiB
+    if (P.nbins <= lo::kWBSmemWords) {
+        slots_log2 = 0;
+        while (slots_log2 < 5 && (P.nbins << (slots_log2 + 1)) <= lo::kWBSmemWords) ++slots_log2;
+    } else if (P.nbins <= lo::kWBSmemWordsMax) {
+        slots_log2 = 0;
+    }
+    const size_t smem = slots_log2 >= 0 ? (size_t)(P.nbins << slots_log2) * 4 : 16;
+    // chunk of a column per CTA: ~4 waves of CTAs (2 resident per SM), whole loop rounds, 32-bit counters cannot wrap
+    const int64_t slots = (int64_t)ctx->sm_count * 2;
+    int64_t want = (in->nrows * (int64_t)P.k) / (4 * slots);
+    want = std::max<int64_t>(lo::kWBRoundRows, std::min<int64_t>(want, (int64_t)1 << 24));
+    const int64_t chunk_rows = (want / lo::kWBRoundRows) * lo::kWBRoundRows;
+    const unsigned chunks_per_col = (unsigned)((in->nrows + chunk_rows - 1) / chunk_rows);
+    const unsigned long long blocks = (unsigned long long)chunks_per_col * (unsigned)P.k;
+    if (blocks > 0x7fffffffull) return fail(LO_ERR_INVALID, "table too large for one launch (%llu chunks)", blocks);
+    const char *ib = in->base;
+    const long long ip = in->pitch, nr = in->nrows;
+    if (fast) LO_CUDA(launch_kernel(lo::k_project_cast_hist_bins<OUT, true>, (unsigned)blocks, (unsigned)lo::kWBThreads, smem, s, G.overlap != 0,
+                                    ib, ip, out_base, out_pitch, nr, chunks_per_col, (long long)chunk_rows, slots_log2, (int)aligned, counts, P, G));
+    else      LO_CUDA(launch_kernel(lo::k_project_cast_hist_bins<OUT, false>, (unsigned)blocks, (unsigned)lo::kWBThreads, smem, s, G.overlap != 0,
+                                    ib, ip, out_base, out_pitch, nr, chunks_per_col, (long long)chunk_rows, slots_log2, (int)aligned, counts, P, G));
+    LO_CUDA(cudaGetLastError());
+    ctx->launches.fetch_add(1, std::memory_order_relaxed);
+    return LO_OK;
+}
+
 int project_cast_hist_impl(lo_ctx *ctx, const lo_table *in, const int32_t *col_idx, int32_t k,
                            lo_table *out, const lo_hist_spec *spec, uint64_t *counts_dev, cudaStream_t s,
                            const lo::GroupStep *group = nullptr) {
@@ -314,7 +355,11 @@ int project_cast_hist_impl(lo_ctx *ctx, const lo_table *in, const int32_t *col_i
         }
         unsigned long long *cnt = spec ? (unsigned long long *)counts_dev + (int64_t)c0 * spec->nbins : nullptr;
         int rc;
-        if (spec) {
+        if (spec && spec->nbins > LO_TILE_BINS) {
+            if (out_mode == 0)      rc = launch_f64_bins<0>(ctx, in, out, c0, P, cnt, aligned, G, s);
+            else if (out_mode == 1) rc = launch_f64_bins<1>(ctx, in, out, c0, P, cnt, aligned, G, s);
+            else                    rc = launch_f64_bins<2>(ctx, in, out, c0, P, cnt, aligned, G, s);
+        } else if (spec) {
             if (out_mode == 0)      rc = launch_f64<0, true>(ctx, in, out, c0, P, cnt, aligned, G, s);
             else if (out_mode == 1) rc = launch_f64<1, true>(ctx, in, out, c0, P, cnt, aligned, G, s);
             else                    rc = launch_f64<2, true>(ctx, in, out, c0, P, cnt, aligned, G, s);

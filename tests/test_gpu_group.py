@@ -59,6 +59,10 @@ def _worker(rank, world, port, merge, ret):
     got["f64_overlap"] = c.to_numpy() if sh.has_result else None
     got["f64_bcast"] = sh.project_cast_hist(table, cols, 10, lo4, hi4, bcast=True).to_numpy()
     got["sums"] = [out.checksum(j) for j in range(4)]
+    # more than 256 bins: the chunk kernel takes part in the same merge (1000 bins: in-kernel arrival and epilogue;
+    # 30 000 bins x 4 columns: L2 counters, the root's epilogue as its own launch), two steps each through both buffers
+    got["f64_1000"] = [sh.project_cast_hist(table, cols, 1000, lo4, hi4, bcast=True).to_numpy() for _ in range(2)][-1]
+    got["f64_30000"] = [sh.project_cast_hist(table, cols, 30000, lo4, hi4, bcast=True, independent=True).to_numpy() for _ in range(2)][-1]
     # range pre-pass over all shards (always delivered everywhere)
     got["minmax"] = [a.tolist() for a in sh.minmax_cast(table, cols)]
     # u8: 300 columns x 256 bins = 76 800 counts -> the root's epilogue is its own multi-CTA launch
@@ -123,7 +127,11 @@ def _check(res, world, merge):
         np.testing.assert_array_equal(c, exp)
     np.testing.assert_array_equal(res[0]["f64_overlap"], exp)
     total = [0] * 4
+    exp1000, _ = cport.synth_project_cast_hist(1, SEED, 0, rows, -1000.0, 1000.0, cols, 1000, lo4, hi4)
+    exp30000, _ = cport.synth_project_cast_hist(1, SEED, 0, rows, -1000.0, 1000.0, cols, 30000, lo4, hi4)
     for r in range(world):
+        np.testing.assert_array_equal(res[r]["f64_1000"], exp1000)
+        np.testing.assert_array_equal(res[r]["f64_30000"], exp30000)
         np.testing.assert_array_equal(res[r]["f64_bcast"], exp10)        # all-reduce semantics: every rank has it
         total = [(a + b) & 0xFFFFFFFFFFFFFFFF for a, b in zip(total, res[r]["sums"])]
     assert total == [int(s) for s in sums]      # fp32 output slabs, position-weighted checksums of the shards add up

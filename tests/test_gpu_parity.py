@@ -52,6 +52,46 @@ def test_nbins(engine, nbins):
     _check_project_cast_hist(engine, table, [0, 1, 2], nbins, -1000.0, 1000.0)
 
 
+@pytest.mark.parametrize("nbins", [257, 512, 1000, 4096, 16384, 16385, 40000, 57344, 57345, 65536])
+def test_nbins_above_the_tile_kernel(engine, nbins):
+    """More than 256 bins (the REST ``bins`` key has no 256 ceiling): the chunk kernel with 32-bit shared-memory lane slots
+    (<= 16 Ki bins) or L2 counters (above), same binning arithmetic, bit-exact against the oracle; fp32 out, histogram
+    only, fp64 copy, special values, per-column ranges, a constant column and a ragged row count."""
+    table = bn.synth_table_f64(1, SEED + 31, 4, 1000, 333_337)
+    _check_project_cast_hist(engine, table, [0, 1, 2, 3], nbins, -1000.0, 1000.0)
+    _check_project_cast_hist(engine, table, [3, 0], nbins, np.array([-1000, -3.5], np.float32), np.array([7.25, 1000], np.float32),
+                             with_out=False)
+    _check_project_cast_hist(engine, table, [2], nbins, -1e30, 1e30, out_dtype="f64")
+    const = bn.synth_table_f64(2, SEED, 2, 0, 70_001)
+    c = _check_project_cast_hist(engine, const, [0, 1], nbins, -1000.0, 1000.0)
+    assert c[0].max() >= 70_001 - 100
+
+
+def test_nbins_above_the_tile_kernel_unaligned_and_host(engine):
+    nrows, ncols, nbins = 100_003, 3, 1000
+    table = bn.synth_table_f64(1, SEED, ncols, 0, nrows)
+    big = engine.table("f64", (nrows + 1) * ncols + 8, 1)
+    flat = np.zeros((nrows + 1) * ncols + 8)
+    for c in range(ncols):
+        flat[1 + c * (nrows + 1): 1 + c * (nrows + 1) + nrows] = table[c]
+    big.upload(0, flat)
+    view = engine.wrap("f64", nrows, ncols, big.base_ptr + 8, (nrows + 1) * 8)
+    out = engine.table("f32", nrows, ncols)
+    counts = engine.project_cast_hist(view, [2, 0, 1], nbins, -1000.0, 1000.0, out=out).to_numpy()
+    exp_out, exp_counts = bn.project_cast_hist(table, [2, 0, 1], nbins, [-1000.0] * 3, [1000.0] * 3)
+    np.testing.assert_array_equal(counts, exp_counts)
+    for j in range(3):
+        np.testing.assert_array_equal(_bits(out.to_numpy(j)), _bits(exp_out[j]))
+    view.free(); out.free(); big.free()
+    outs = [np.empty(nrows, dtype=np.float32) for _ in range(ncols)]
+    lo = np.full(ncols, -1000, np.float32); hi = np.full(ncols, 1000, np.float32)
+    hc, _ = engine.project_cast_hist_host([table[j] for j in range(ncols)], 5000, lo, hi, out=outs)
+    exp_out, exp_counts = bn.project_cast_hist(table, range(ncols), 5000, lo, hi)
+    np.testing.assert_array_equal(hc, exp_counts)
+    for j in range(ncols):
+        np.testing.assert_array_equal(_bits(outs[j]), _bits(exp_out[j]))
+
+
 def test_special_values_and_per_column_ranges(engine):
     nrows = 300_000
     table = bn.synth_table_f64(1, SEED + 2, 8, 0, nrows)
@@ -246,7 +286,7 @@ def test_error_reporting(engine):
         engine.project_cast_hist(t, [0, 2], 256, -1.0, 1.0)
     assert e.value.code == LO_ERR_INVALID and "col_idx" in e.value.message
     with pytest.raises(LoexecError):
-        engine.project_cast_hist(t, [0], 257, -1.0, 1.0)
+        engine.project_cast_hist(t, [0], 65537, -1.0, 1.0)
     with pytest.raises(LoexecError):
         engine.project_cast_hist(t, [0], 10, 1.0, 1.0)
     with pytest.raises(LoexecError):
