@@ -461,6 +461,13 @@ def test_rest_binned_histogram_shards_over_every_visible_gpu(built, tmp_path):
         assert r.status_code == 201 and eng.resident.hits >= 1
         got = [d for d in db.find("h2", {}) if d["_id"] != 0][0]["c"]["counts"]
         assert got == bn.hist_f32(bn.cast_f64_f32(cols["c"]), np.float32(0), np.float32(1000), 10).tolist()
+        # ``bins`` above the tile kernel's 256: same route, the chunk kernel and the same in-kernel merge
+        r = c.post("/histograms", json={"inputDatasetName": "d", "outputDatasetName": "h3", "names": ["a", "c"], "bins": 2000,
+                                        "range": [-200, 1000]})
+        assert r.status_code == 201 and db.find_one("h3", {"_id": 0})["finished"] is True
+        docs3 = {list(d)[0]: d[list(d)[0]] for d in db.find("h3", {}) if d["_id"] != 0}
+        for name in ("a", "c"):
+            assert docs3[name]["counts"] == bn.hist_f32(bn.cast_f64_f32(cols[name]), np.float32(-200), np.float32(1000), 2000).tolist()
         assert eng.timeouts() == 0
 
 
