@@ -19,6 +19,11 @@
 //     uniform one).  A thread handles <= 255 elements per tile so a byte never wraps; the CTA then folds the 256
 //     private histograms (LDS.128, packed 16-bit adds, a transposing warp butterfly) and issues one RED.64 per
 //     non-empty bin.
+//   * byte columns (k_hist_u8_cols_lanes, the shipped K4) and histograms of more than 256 bins
+//     (k_project_cast_hist_bins) drop the byte fields: 32-bit counters in lane slots shared by the CTA's warps, bank =
+//     lane, the counter address one PRMT (bytes) or one shift-add (bins) away from the value, ONE ATOMS per element, a
+//     CTA streams a long chunk of its column and folds once.  The per-thread byte-counter variants of K4
+//     (k_hist_u8_cols<ALIGNED, MODE>) stay behind LOEXEC_U8_MODE as the measured history.
 //   * several GPUs (GroupStep): the bins go to the device's own matrix; the CTA finishing a column's last tile pushes
 //     the column to the root GPU with system-scope RED.64 over NVLink, the last pusher arrives, the root's last CTA
 //     moves the merged matrix out — merge, arrival and epilogue ride inside the one streaming launch per step.
