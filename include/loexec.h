@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define LO_ABI_VERSION 2
+#define LO_ABI_VERSION 3
 
 #define LO_OK                    0
 #define LO_ERR_INVALID          -1   /* bad argument (message says which)              */
@@ -92,6 +92,8 @@ typedef struct lo_host_timing {
     double h2d_bytes;  /* bytes copied host -> device                    */
     double d2h_bytes;  /* bytes copied device -> host                    */
     int64_t launches;  /* kernels launched                               */
+    double kernel_ms;  /* device time of the call's kernels between two events on its stream (parser, group-by); 0 for the
+                          chunked pipelines, whose kernels overlap their copies   */
 } lo_host_timing;
 
 /* ---- context ------------------------------------------------------------------------- */

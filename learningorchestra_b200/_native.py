@@ -33,7 +33,7 @@ LO_GROUP_BLOB_BYTES = 512
 LO_GROUP_MAX_DEVICES = 16
 LO_GROUP_MAX_COUNTS = 262144
 LO_NUM_FLOAT, LO_NUM_INTEGER, LO_NUM_EMPTY, LO_NUM_INVALID, LO_NUM_UNSUPPORTED = 0, 1, 2, 3, 4
-LO_ABI_VERSION = 2
+LO_ABI_VERSION = 3
 
 _ERR_NAMES = {
     LO_ERR_INVALID: "LO_ERR_INVALID", LO_ERR_CUDA: "LO_ERR_CUDA", LO_ERR_NOMEM: "LO_ERR_NOMEM",
@@ -58,7 +58,7 @@ class HistSpec(C.Structure):
 
 class HostTiming(C.Structure):
     _fields_ = [("total_ms", C.c_double), ("h2d_bytes", C.c_double), ("d2h_bytes", C.c_double),
-                ("launches", C.c_int64)]
+                ("launches", C.c_int64), ("kernel_ms", C.c_double)]
 
 
 # every symbol include/loexec.h declares: name -> (restype, argtypes)

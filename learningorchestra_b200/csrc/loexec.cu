@@ -584,6 +584,14 @@ int lo_init(int device, lo_ctx **out) {
     ctx->stream = nullptr;
     auto setup = [&]() -> int {
         LO_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        // scratch of the parser / group-by calls comes from the device's stream-ordered pool: keep up to 8 GiB of it
+        // mapped between calls (the default threshold of 0 hands everything back at every synchronise, and the next
+        // call pays the mapping again: ~5 ms of a 9 ms call on 20 M rows)
+        cudaMemPool_t pool = nullptr;
+        LO_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+        uint64_t keep = 8ull << 30;
+        if (const char *e = getenv("LOEXEC_POOL_KEEP_MB")) keep = (uint64_t)std::max<long long>(0, atoll(e)) << 20;
+        LO_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
         return configure_kernels();
     };
     if (const char *e = getenv("LOEXEC_TMA")) ctx->use_tma.store(e[0] == '1');
@@ -963,6 +971,31 @@ int copy_cols(char *dev_base, int64_t dev_pitch, const void *const *host_cols, i
     return LO_OK;
 }
 
+// kernel time of a *_host call that runs its kernels once (parser, group-by): two events on the call's stream
+struct DevTimer {
+    cudaEvent_t a = nullptr, b = nullptr;
+    cudaError_t start(cudaStream_t s) {
+        cudaError_t e = cudaEventCreate(&a);
+        if (e == cudaSuccess) e = cudaEventCreate(&b);
+        if (e == cudaSuccess) e = cudaEventRecord(a, s);
+        return e;
+    }
+    cudaError_t stop(cudaStream_t s) { return cudaEventRecord(b, s); }
+    double ms() const {                       // after the stream was synchronised
+        float t = 0.f;
+        return (a && b && cudaEventElapsedTime(&t, a, b) == cudaSuccess) ? (double)t : 0.0;
+    }
+    ~DevTimer() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+};
+
+// scratch of one call: allocated and freed in stream order (cudaMallocAsync / cudaFreeAsync on the call's stream), so a
+// call neither synchronises the device (cudaFree does) nor touches the legacy default stream (cudaMemcpy does) — other
+// jobs' streams keep running
+template <typename T>
+cudaError_t scratch_alloc(T **p, size_t bytes, cudaStream_t s) { return cudaMallocAsync((void **)p, bytes ? bytes : 1, s); }
+template <typename T>
+void scratch_free(T *p, cudaStream_t s) { if (p) cudaFreeAsync((void *)p, s); }
+
 template <typename Launch>
 int host_pipeline(lo_ctx *ctx, const void *const *in_cols, int in_dtype, int64_t nrows, int32_t k,
                   void *const *out_cols, int out_dtype, int64_t tile_rows, size_t ncounts, uint64_t *counts_host,
@@ -1026,6 +1059,7 @@ int host_pipeline(lo_ctx *ctx, const void *const *in_cols, int in_dtype, int64_t
         timing->h2d_bytes = h2d;
         timing->d2h_bytes = d2h;
         timing->launches  = ctx->launches.load() - launches0;
+        timing->kernel_ms = 0.0;      // chunks overlap their copies: there is no separate kernel time to report
     }
     return LO_OK;
 }
@@ -1119,11 +1153,13 @@ int lo_value_counts_f64_host(lo_ctx *ctx, const double *values, int64_t n, doubl
     unsigned long long *d_keys = nullptr, *d_counts = nullptr, *d_out = nullptr;
     const size_t out_n = (size_t)std::max<int64_t>(capacity, 1);
     cudaStream_t s = ctx->stream;
-    cudaError_t e = cudaMalloc((void **)&d_val, (size_t)n * 8);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&d_keys, slots * 8);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&d_counts, slots * 8);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&d_out, (2 * out_n + 1) * 8);
+    DevTimer kt;
+    cudaError_t e = scratch_alloc(&d_val, (size_t)n * 8, s);
+    if (e == cudaSuccess) e = scratch_alloc(&d_keys, slots * 8, s);
+    if (e == cudaSuccess) e = scratch_alloc(&d_counts, slots * 8, s);
+    if (e == cudaSuccess) e = scratch_alloc(&d_out, (2 * out_n + 1) * 8, s);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_val, values, (size_t)n * 8, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = kt.start(s);
     if (e == cudaSuccess) e = cudaMemsetAsync(d_keys, 0xFF, slots * 8, s);
     if (e == cudaSuccess) e = cudaMemsetAsync(d_counts, 0, slots * 8, s);
     if (e == cudaSuccess) e = cudaMemsetAsync(d_out + 2 * out_n, 0, 8, s);
@@ -1135,13 +1171,15 @@ int lo_value_counts_f64_host(lo_ctx *ctx, const double *values, int64_t n, doubl
         e = cudaGetLastError();
         ctx->launches.fetch_add(2, std::memory_order_relaxed);
     }
+    if (e == cudaSuccess) e = kt.stop(s);
     unsigned long long nd = 0;
     if (e == cudaSuccess) e = cudaMemcpyAsync(&nd, d_out + 2 * out_n, 8, cudaMemcpyDeviceToHost, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     const size_t take = (size_t)std::min<unsigned long long>(nd, (unsigned long long)capacity);
-    if (e == cudaSuccess && take) e = cudaMemcpy(keys_out, d_out, take * 8, cudaMemcpyDeviceToHost);
-    if (e == cudaSuccess && take) e = cudaMemcpy(counts_out, d_out + out_n, take * 8, cudaMemcpyDeviceToHost);
-    cudaFree(d_val); cudaFree(d_keys); cudaFree(d_counts); cudaFree(d_out);
+    if (e == cudaSuccess && take) e = cudaMemcpyAsync(keys_out, d_out, take * 8, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess && take) e = cudaMemcpyAsync(counts_out, d_out + out_n, take * 8, cudaMemcpyDeviceToHost, s);
+    scratch_free(d_val, s); scratch_free(d_keys, s); scratch_free(d_counts, s); scratch_free(d_out, s);
+    { const cudaError_t e2 = cudaStreamSynchronize(s); if (e == cudaSuccess) e = e2; }
     if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? LO_ERR_NOMEM : LO_ERR_CUDA, "value_counts_f64: %s", cudaGetErrorString(e));
     *ndistinct = (int64_t)nd;
     if (timing) {
@@ -1149,6 +1187,7 @@ int lo_value_counts_f64_host(lo_ctx *ctx, const double *values, int64_t n, doubl
         timing->h2d_bytes = (double)n * 8;
         timing->d2h_bytes = (double)take * 16 + 8;
         timing->launches  = ctx->launches.load() - launches0;
+        timing->kernel_ms = kt.ms();
     }
     if ((int64_t)nd > capacity)
         return fail(LO_ERR_INVALID, "%llu distinct keys do not fit the caller's capacity %lld", nd, (long long)capacity);
@@ -1179,13 +1218,15 @@ int lo_value_counts_str_host(lo_ctx *ctx, const uint8_t *chars, const int64_t *o
     long long *d_off = nullptr;
     unsigned long long *d_slots = nullptr, *d_counts = nullptr, *d_out = nullptr;
     cudaStream_t s = ctx->stream;
-    cudaError_t e = cudaMalloc((void **)&d_chars, (size_t)std::max<int64_t>(nbytes, 1));
-    if (e == cudaSuccess) e = cudaMalloc((void **)&d_off, (size_t)(n + 1) * 8);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&d_slots, nslots * 8);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&d_counts, nslots * 8);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&d_out, (2 * out_n + 1) * 8);
+    DevTimer kt;
+    cudaError_t e = scratch_alloc(&d_chars, (size_t)nbytes, s);
+    if (e == cudaSuccess) e = scratch_alloc(&d_off, (size_t)(n + 1) * 8, s);
+    if (e == cudaSuccess) e = scratch_alloc(&d_slots, nslots * 8, s);
+    if (e == cudaSuccess) e = scratch_alloc(&d_counts, nslots * 8, s);
+    if (e == cudaSuccess) e = scratch_alloc(&d_out, (2 * out_n + 1) * 8, s);
     if (e == cudaSuccess && nbytes) e = cudaMemcpyAsync(d_chars, chars, (size_t)nbytes, cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_off, offsets, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = kt.start(s);
     if (e == cudaSuccess) e = cudaMemsetAsync(d_slots, 0xFF, nslots * 8, s);
     if (e == cudaSuccess) e = cudaMemsetAsync(d_counts, 0, nslots * 8, s);
     if (e == cudaSuccess) e = cudaMemsetAsync(d_out + 2 * out_n, 0, 8, s);
@@ -1197,13 +1238,15 @@ int lo_value_counts_str_host(lo_ctx *ctx, const uint8_t *chars, const int64_t *o
         e = cudaGetLastError();
         ctx->launches.fetch_add(2, std::memory_order_relaxed);
     }
+    if (e == cudaSuccess) e = kt.stop(s);
     unsigned long long nd = 0;
     if (e == cudaSuccess) e = cudaMemcpyAsync(&nd, d_out + 2 * out_n, 8, cudaMemcpyDeviceToHost, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     const size_t take = (size_t)std::min<unsigned long long>(nd, (unsigned long long)capacity);
-    if (e == cudaSuccess && take) e = cudaMemcpy(rep_rows_out, d_out, take * 8, cudaMemcpyDeviceToHost);
-    if (e == cudaSuccess && take) e = cudaMemcpy(counts_out, d_out + out_n, take * 8, cudaMemcpyDeviceToHost);
-    cudaFree(d_chars); cudaFree(d_off); cudaFree(d_slots); cudaFree(d_counts); cudaFree(d_out);
+    if (e == cudaSuccess && take) e = cudaMemcpyAsync(rep_rows_out, d_out, take * 8, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess && take) e = cudaMemcpyAsync(counts_out, d_out + out_n, take * 8, cudaMemcpyDeviceToHost, s);
+    scratch_free(d_chars, s); scratch_free(d_off, s); scratch_free(d_slots, s); scratch_free(d_counts, s); scratch_free(d_out, s);
+    { const cudaError_t e2 = cudaStreamSynchronize(s); if (e == cudaSuccess) e = e2; }
     if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? LO_ERR_NOMEM : LO_ERR_CUDA, "value_counts_str: %s", cudaGetErrorString(e));
     *ndistinct = (int64_t)nd;
     if (timing) {
@@ -1211,6 +1254,7 @@ int lo_value_counts_str_host(lo_ctx *ctx, const uint8_t *chars, const int64_t *o
         timing->h2d_bytes = (double)nbytes + (double)(n + 1) * 8;
         timing->d2h_bytes = (double)take * 16 + 8;
         timing->launches  = ctx->launches.load() - launches0;
+        timing->kernel_ms = kt.ms();
     }
     if ((int64_t)nd > capacity)
         return fail(LO_ERR_INVALID, "%llu distinct keys do not fit the caller's capacity %lld", nd, (long long)capacity);
@@ -1236,10 +1280,11 @@ int lo_parse_number_host(lo_ctx *ctx, const uint8_t *chars, const int64_t *offse
     long long *d_off = nullptr;
     unsigned long long *d_val = nullptr;
     cudaStream_t s = ctx->stream;
-    cudaError_t e = cudaMalloc((void **)&d_chars, (size_t)std::max<int64_t>(nbytes, 1));
-    if (e == cudaSuccess) e = cudaMalloc((void **)&d_off, (size_t)(n + 1) * 8);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&d_val, (size_t)n * 8);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&d_status, (size_t)n);
+    DevTimer kt;
+    cudaError_t e = scratch_alloc(&d_chars, (size_t)nbytes, s);
+    if (e == cudaSuccess) e = scratch_alloc(&d_off, (size_t)(n + 1) * 8, s);
+    if (e == cudaSuccess) e = scratch_alloc(&d_val, (size_t)n * 8, s);
+    if (e == cudaSuccess) e = scratch_alloc(&d_status, (size_t)n, s);
     if (e == cudaSuccess && nbytes) e = cudaMemcpyAsync(d_chars, chars + offsets[0], (size_t)nbytes, cudaMemcpyHostToDevice, s);
     std::vector<int64_t> rel;
     const int64_t *off_src = offsets;
@@ -1249,22 +1294,25 @@ int lo_parse_number_host(lo_ctx *ctx, const uint8_t *chars, const int64_t *offse
         off_src = rel.data();
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_off, off_src, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = kt.start(s);
     if (e == cudaSuccess) {
         const int grid = (int)std::min<int64_t>((n + 127) / 128, (int64_t)ctx->sm_count * 16);
         lo::k_parse_number<<<grid, 128, 0, s>>>(d_chars, d_off, n, d_val, d_status);
         e = cudaGetLastError();
         ctx->launches.fetch_add(1, std::memory_order_relaxed);
     }
+    if (e == cudaSuccess) e = kt.stop(s);
     if (e == cudaSuccess) e = cudaMemcpyAsync(values, d_val, (size_t)n * 8, cudaMemcpyDeviceToHost, s);
     if (e == cudaSuccess) e = cudaMemcpyAsync(status, d_status, (size_t)n, cudaMemcpyDeviceToHost, s);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-    cudaFree(d_chars); cudaFree(d_off); cudaFree(d_val); cudaFree(d_status);
+    scratch_free(d_chars, s); scratch_free(d_off, s); scratch_free(d_val, s); scratch_free(d_status, s);
+    { const cudaError_t e2 = cudaStreamSynchronize(s); if (e == cudaSuccess) e = e2; }
     if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? LO_ERR_NOMEM : LO_ERR_CUDA, "parse_number: %s", cudaGetErrorString(e));
     if (timing) {
         timing->total_ms  = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         timing->h2d_bytes = (double)nbytes + (double)(n + 1) * 8;
         timing->d2h_bytes = (double)n * 9;
         timing->launches  = ctx->launches.load() - launches0;
+        timing->kernel_ms = kt.ms();
     }
     return LO_OK;
 }
