@@ -603,14 +603,15 @@ k_project_cast_hist(const char *__restrict__ in_base, long long in_pitch,
 // are 32-bit words in shared memory, nbins x S lane slots (S = the largest power of two <= 32 with nbins * S <= 16 Ki
 // words; slot = lane mod S, so S = 32 is conflict-free and smaller S spreads equal bins of one instruction over S
 // words), one ATOMS per element; up to 56 Ki bins one slot per bin in 224 KiB (one CTA per SM); above that the increments go
-// straight to the count matrix in L2 (RED.64: with that many bins two lanes rarely meet).  A CTA streams a chunk of one projected column and folds once (32-bit
+// straight to the count matrix in L2 (RED.64: with that many bins two lanes rarely meet).  A CTA streams a chunk of one projected column, four 32-byte vectors in flight per thread, and folds once (32-bit
 // counters: chunk_rows < 2^31).  HBM-bound like the 256-bin kernel: 12 B and one shared-memory atomic per element.
 // grid.x = k * chunks_per_col
 // ---------------------------------------------------------------------------------------------
 constexpr int kWBThreads   = 512;
 constexpr int kWBSmemWords = 16384;                                  // 64 KiB: two CTAs per SM
 constexpr int kWBSmemWordsMax = 57344;                               // 224 KiB: one CTA per SM, one slot per bin
-constexpr int kWBRoundRows = kWBThreads * kVec * 2;                  // two 32-byte vectors per thread per loop round
+constexpr int kWBVecs      = 4;                                      // 32-byte vectors in flight per thread
+constexpr int kWBRoundRows = kWBThreads * kVec * kWBVecs;            // rows per loop round
 
 template <int OUT, bool FASTDIV>
 __global__ void __launch_bounds__(kWBThreads, 2)
@@ -651,11 +652,11 @@ k_project_cast_hist_bins(const char *__restrict__ in_base, long long in_pitch, c
         const double *src = in + (long long)threadIdx.x * kVec;
 #pragma unroll 1
         for (; done + kWBRoundRows <= n; done += kWBRoundRows) {
-            double v[2][4];
-            ldg256_stream(src + done, v[0]);
-            ldg256_stream(src + done + (long long)kWBThreads * kVec, v[1]);
+            double v[kWBVecs][4];
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
+            for (int u = 0; u < kWBVecs; ++u) ldg256_stream(src + done + (long long)u * kWBThreads * kVec, v[u]);
+#pragma unroll
+            for (int u = 0; u < kWBVecs; ++u) {
                 const long long e = done + ((long long)u * kWBThreads + threadIdx.x) * kVec;
                 const float f0 = cast_f64_f32(v[u][0]), f1 = cast_f64_f32(v[u][1]), f2 = cast_f64_f32(v[u][2]), f3 = cast_f64_f32(v[u][3]);
                 if (OUT == 1) stg128_stream(out32 + e, f0, f1, f2, f3);

@@ -1,2 +1,2 @@
-timeout 900 python -m pytest tests -m gpu -x -q -k "parse or value_count or executors or number or columnar or group_by or hash" 2>&1 | tail -3
-timeout 600 python scripts/aux_bench.py 2>&1 | tail -75
+timeout 900 python -m pytest tests -m gpu -x -q -k "nbins or group" 2>&1 | tail -3
+timeout 300 python scripts/bins_bench.py 2>&1 | tail -9
