@@ -953,7 +953,7 @@ int copy_cols(char *dev_base, int64_t dev_pitch, const void *const *host_cols, i
     for (int32_t j = 0; j < k;) {
         int32_t e = j + 1;
         const ptrdiff_t stride = (e < k) ? (const char *)host_cols[e] - (const char *)host_cols[j] : 0;
-        if (stride >= (ptrdiff_t)bytes && stride <= (ptrdiff_t)0x7fffffff)
+        if (stride >= (ptrdiff_t)bytes && stride <= (ptrdiff_t)0x7fffffff && dev_pitch <= 0x7fffffffll)   // cudaMemcpy2D pitch limit
             while (e < k && (const char *)host_cols[e] - (const char *)host_cols[e - 1] == stride) ++e;
         else
             e = j + 1;
