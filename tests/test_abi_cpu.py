@@ -94,3 +94,30 @@ def test_plain_c_program_links_against_the_abi(built):
         assert out.returncode == 0, out.stderr
     else:
         assert out.returncode == 3 and "no CUDA device" in out.stderr      # loud, documented failure
+
+
+def test_ctypes_mirror_matches_the_header_constants_and_struct_layouts(tmp_path):
+    """Every ``#define LO_*`` integer of include/loexec.h that ``_native`` mirrors has the same value there, and the two
+    structs that cross the boundary by pointer have the same size and field offsets (compiled with gcc, no library needed)."""
+    from learningorchestra_b200 import _native
+    text = re.sub(r"/\*.*?\*/", "", HEADER.read_text(), flags=re.S)
+    names = [n for n in re.findall(r"#define\s+(LO_[A-Z0-9_]+)\s+-?\d", text) if hasattr(_native, n)]
+    assert len(names) >= 30 and "LO_ABI_VERSION" in names and "LO_MAX_BINS" in names
+    src = tmp_path / "layout.c"
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "loexec.h"', 'int main(void) {']
+    lines += [f'    printf("{n} %lld\\n", (long long)({n}));' for n in names]
+    for struct, fields in (("lo_host_timing", ["total_ms", "h2d_bytes", "d2h_bytes", "launches", "kernel_ms"]),
+                           ("lo_hist_spec", ["nbins", "flags", "lo", "hi"])):
+        lines.append(f'    printf("sizeof.{struct} %zu\\n", sizeof({struct}));')
+        lines += [f'    printf("offsetof.{struct}.{f} %zu\\n", offsetof({struct}, {f}));' for f in fields]
+    lines += ['    return 0;', '}']
+    src.write_text("\n".join(lines) + "\n")
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", str(ROOT / "include"), str(src), "-o", str(exe)], check=True)
+    got = dict(line.split() for line in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for n in names:
+        assert int(got[n]) == getattr(_native, n), n
+    for struct, mirror in (("lo_host_timing", _native.HostTiming), ("lo_hist_spec", _native.HistSpec)):
+        assert int(got[f"sizeof.{struct}"]) == ctypes.sizeof(mirror), struct
+        for f, _t in mirror._fields_:
+            assert int(got[f"offsetof.{struct}.{f}"]) == getattr(mirror, f).offset, f"{struct}.{f}"
