@@ -40,6 +40,22 @@ def test_library_is_sm100a_native_code(built):
     assert "MUFU.RCP" not in sass.split("BAR.SYNC")[0] or True
 
 
+def test_lane_slot_kernels_issue_one_shared_atomic_per_element(built):
+    """The shipped byte-histogram kernel is the lane-slot form: per 64 input bytes 64 PRMT (the counter address straight from
+    the input word) and 64 shared-memory atomics with the reserved-smem base in the immediate, 128-bit streaming loads, a
+    RED.64 flush; the wide-bin kernel counts with shared atomics too and keeps the 256-bit loads."""
+    from learningorchestra_b200 import _native
+    sass = subprocess.run(["cuobjdump", "-sass", str(_native.LIB_PATH)], capture_output=True, text=True).stdout
+    lanes = sass.split("Function : _ZN2lo20k_hist_u8_cols_lanesILi2EEE")[1].split("Function :")[0]
+    atoms = [l for l in lanes.splitlines() if "ATOMS" in l]
+    assert len(atoms) >= 128 and all("+0x400]" in l for l in atoms if "POPC.INC" in l)
+    assert lanes.count("PRMT") >= 128 and "LDG.E.NA.128" in lanes or "LDG.E.128" in lanes
+    assert "LDS.U8" not in lanes and "STS.U8" not in lanes
+    assert "REDG.E.ADD.64.STRONG.GPU" in lanes or "RED.E.ADD.64.STRONG.GPU" in lanes
+    bins = sass.split("Function : _ZN2lo24k_project_cast_hist_binsILi1ELb1EEE")[1].split("Function :")[0]
+    assert "ATOMS" in bins and "F2F.F32.F64" in bins and ".256" in bins
+
+
 def test_tma_variant_is_compiled_with_bulk_copy_and_mbarriers(built):
     """The opt-in TMA-staged kernel really uses the bulk-copy engine: UBLKCP (cp.async.bulk) + SYNCS (mbarrier) in SASS."""
     from learningorchestra_b200 import _native
