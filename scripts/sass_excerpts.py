@@ -10,6 +10,7 @@ KERNELS = {
     "k_project_cast_hist_tma": "_ZN2lo23k_project_cast_hist_tmaILi1ELb1ELb1EEE",
     "k_hist_u8_cols": "_ZN2lo14k_hist_u8_colsILb1ELi%sEEE" % (sys.argv[1] if len(sys.argv) > 1 else "7"),
     "hist_u8_lanes": "_ZN2lo20k_hist_u8_cols_lanesILi2EEE",
+    "k_project_cast_hist_bins": "_ZN2lo24k_project_cast_hist_binsILi1ELb1EEE",
     "k_group_merge_big": "_ZN2lo17k_group_merge_bigE",
 }
 PAT = re.compile(r"\b(PRMT|VOTE|LDG|STG|RED|REDG|ATOMG|ATOMS|ATOM|UBLKCP|SYNCS|LDS|STS|MEMBAR|PREEXIT|ACQBULK|F2F|CCTL|ERRBAR|FENCE|IMMA|HMMA|UTMALDG|UTCHMMA)[A-Z0-9_.]*")
