@@ -33,6 +33,15 @@ class ResidentDataset:
         return self.table.pitch_bytes * self.table.ncols
 
 
+def device_number_column(values: np.ndarray, valid: np.ndarray, is_int: np.ndarray):
+    """(float64 slab, valid mask, "int" | "float") of a stored number column for the HBM-resident copy: nulls become NaN
+    (the kernels skip them), a fully valid column is handed over as it is (no copy), and the int / float kind is read
+    without materialising the valid subset.  Same result as ``np.where(valid, values, nan)`` / ``is_int[valid].all()``."""
+    if valid.all():
+        return values, valid, "int" if is_int.all() else "float"
+    return np.where(valid, values, np.nan), valid, "int" if bool((is_int | ~valid).all()) else "float"
+
+
 class ResidentTables:
     def __init__(self, engine, max_bytes: int = 64 << 30):
         self.engine, self.max_bytes = engine, max_bytes
@@ -96,7 +105,7 @@ class ResidentTables:
                     if c is not None and c.kind == "object":
                         packed = columnar.numeric_column(c.to_pylist())
                     elif c is not None and c.kind == "number":
-                        packed = (np.where(c.valid, c.values, np.nan), c.valid, "int" if c.is_int[c.valid].all() else "float")
+                        packed = device_number_column(c.values, c.valid, c.is_int)
                     else:
                         packed = None
                 else:
@@ -105,7 +114,8 @@ class ResidentTables:
                     if f in fields:
                         raise ValueError(f"field {f!r} is not numeric; run /fieldTypes first")
                     continue                 # a previously resident column that stopped being numeric: drop it
-                names.append(f); cols.append(packed[0]); kinds.append(packed[2]); nulls.append(int((~packed[1]).sum()))
+                names.append(f); cols.append(packed[0]); kinds.append(packed[2])
+                nulls.append(int(packed[1].size - np.count_nonzero(packed[1])))
             table = self.engine.table_from_numpy(cols) if len(rows) and cols else self.engine.table("f64", 0, max(len(cols), 1))
             new = ResidentDataset(version, row_ids, names, kinds, nulls, table)
             new.users = 1

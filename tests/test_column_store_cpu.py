@@ -190,3 +190,23 @@ def test_rest_ingest_route_then_the_three_services(tmp_path):
     assert [d["_id"] for d in page] == [0, 1, 2] and page[0]["finished"] is True and isinstance(page[1]["Fare"], (int, float))
     h = c.get("/files/h?limit=10").get_json()["result"]
     assert [d["_id"] for d in h] == [0, 1, 2] and h[0]["finished"] is True
+
+
+def test_device_number_column_matches_the_plain_formulation():
+    """The packing of a stored number column for the HBM-resident copy (no copy when nothing is null, kind without
+    materialising the valid subset) gives exactly what np.where / boolean indexing give."""
+    from learningorchestra_b200.table_cache import device_number_column
+    rng = np.random.default_rng(5)
+    for n in (0, 1, 7, 1000):
+        for null_rate in (0.0, 0.3, 1.0):
+            for ints in (True, False):
+                values = np.round(rng.uniform(-50, 50, n)) if ints else rng.uniform(-50, 50, n)
+                valid = rng.random(n) >= null_rate
+                is_int = (values == np.round(values)) & valid
+                slab, v, kind = device_number_column(values, valid, is_int)
+                want = np.where(valid, values, np.nan)
+                assert v is valid and np.array_equal(np.isnan(slab[~valid]), np.ones(int((~valid).sum()), bool))
+                assert np.array_equal(slab[valid], want[valid])
+                assert kind == ("int" if is_int[valid].all() else "float")
+                if valid.all():
+                    assert slab is values          # handed over without a copy
