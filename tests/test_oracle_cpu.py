@@ -132,3 +132,20 @@ def test_cast_has_a_third_independent_witness():
     tb[np.isnan(t)] = 0x7FC00000
     np.testing.assert_array_equal(tb, _bits(bn.cast_f64_f32(x)))
     np.testing.assert_array_equal(tb, _bits(cport.cast_f64_f32(x)))
+
+
+@pytest.mark.parametrize("nbins", [257, 1000, 16385, 65536])
+def test_wide_histograms_agree_between_the_two_restatements(nbins):
+    """Above 256 bins (the chunk kernel's territory on the GPU) the C and numpy restatements still agree bit for bit, the
+    streaming variant included, and every in-range finite value lands in exactly one bin."""
+    cols = [3, 0]
+    lo = np.array([-1000.0, -3.5], dtype=np.float32); hi = np.array([7.25, 1000.0], dtype=np.float32)
+    table = bn.synth_table_f64(1, SEED + 5, 4, 250, 40_001)
+    _outs, counts = cport.project_cast_hist([table[c] for c in cols], nbins, lo, hi)
+    exp_out, exp_counts = bn.project_cast_hist(table, cols, nbins, lo, hi)
+    np.testing.assert_array_equal(counts, exp_counts)
+    c2, _sums = cport.synth_project_cast_hist(1, SEED + 5, 250, 40_001, -1000.0, 1000.0, cols, nbins, lo, hi)
+    np.testing.assert_array_equal(c2, exp_counts)
+    for j in range(2):
+        f = exp_out[j]
+        assert int(counts[j].sum()) == int(((f >= lo[j]) & (f <= hi[j])).sum())
